@@ -1,0 +1,392 @@
+// C ABI of the exab200 library (see include/exab200.h for the contract and the reference
+// interfaces each entry point replaces).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/exab200.h"
+#include "k_material.cuh"
+#include "k_operator.cuh"
+#include "material_host.hpp"
+
+using namespace exab;
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& s) { g_err = s; return 1; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+// PA gradient apply configuration: tile of 16 elements (128 threads), 4-stage ring.
+constexpr int kEPT = 16;
+constexpr int kStages = 4;
+}  // namespace
+
+struct exab200_ctx {
+  exab200_config cfg;
+  MatDev mat;
+  int device = 0, sm_count = 148;
+  int* d_e2n = nullptr;
+  unsigned char* d_ess = nullptr;
+  bool have_ess = false;
+  int* d_fail = nullptr;
+  // gradient operator state
+  double grad_dt = 0.0;
+  const double* d_matgrad = nullptr;
+  const double* d_jac = nullptr;
+  double* d_ea = nullptr;  // EA element matrices (assembly == EA)
+  long launches = 0;
+  int ctas_per_sm = 1;
+};
+
+static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((nelems * 8 + threads - 1) / threads); }
+#define NEED_L(c) \
+  if (!(c) || !(c)->d_e2n) return fail("L-vector entry point needs e2n in the config")
+#define POST_LAUNCH(c)          \
+  do {                          \
+    ++(c)->launches;            \
+    CK(cudaPeekAtLastError());  \
+  } while (0)
+
+
+template <int MODE, bool ESS>
+static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
+  using SM = GradMultSmem<kEPT, kStages>;
+  const long ntiles = (c->cfg.nelems + kEPT - 1) / kEPT;
+  long grid = (long)c->sm_count * c->ctas_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  k_grad_mult_pa<kEPT, kStages, MODE, ESS><<<(unsigned)grid, kEPT * 8, sizeof(SM), st>>>(c->d_matgrad, c->d_jac, x, y, io,
+                                                                                          c->cfg.nelems, c->grad_dt);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+
+__global__ void k_set_ess_one(double* __restrict__ v, const unsigned char* __restrict__ ess, long nnodes) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnodes) return;
+  const unsigned m = ess[n];
+  if (m & 1) v[n] = 1.0;
+  if (m & 2) v[nnodes + n] = 1.0;
+  if (m & 4) v[2 * nnodes + n] = 1.0;
+}
+
+
+__global__ void __launch_bounds__(256) k_grad_calc(const double* __restrict__ jac, const double* __restrict__ f,
+                                                   double* __restrict__ out, ElemIO io, long nelems) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;
+  const long e = gt >> 3;
+  const bool active = e < nelems;
+  double c0 = 0, c1 = 0, c2 = 0;
+  if (active) {
+    const long nid = io.e2n[e * 8 + lex_to_native(lane)];
+    c0 = f[nid]; c1 = f[io.nnodes + nid]; c2 = f[2 * io.nnodes + nid];
+  }
+  double d[3][3];
+  nodal_to_qp_grad(c0, lane, d[0][0], d[0][1], d[0][2]);
+  nodal_to_qp_grad(c1, lane, d[1][0], d[1][1], d[1][2]);
+  nodal_to_qp_grad(c2, lane, d[2][0], d[2][1], d[2][2]);
+  if (!active) return;
+  double J[9], adj[9];
+  const long p = e * 8 + lane;
+  for (int i = 0; i < 9; ++i) J[i] = jac[p * 9 + i];
+  const double idet = 1.0 / adjugate(J, adj);
+  for (int t = 0; t < 3; ++t)
+    for (int i = 0; i < 3; ++i)
+      out[p * 9 + t * 3 + i] = (d[i][0] * adj[t] + d[i][1] * adj[3 + t] + d[i][2] * adj[6 + t]) * idet;
+}
+
+
+extern "C" {
+
+const char* exab200_last_error(void) { return g_err.c_str(); }
+int exab200_version(void) { return 100; }
+
+int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
+  if (!cfg || !out) return fail("null argument");
+  if (cfg->nelems <= 0) return fail("nelems must be positive");
+  exab200_ctx* c = new exab200_ctx();
+  c->cfg = *cfg;
+  c->cfg.props = nullptr;
+  c->cfg.e2n = nullptr;
+  std::string msg = build_material(c->mat, cfg->xtal, cfg->slip, cfg->props, cfg->nprops);
+  if (!msg.empty()) { delete c; return fail(msg); }
+  if (cfg->integ == EXAB200_INTEG_BBAR && cfg->assembly == EXAB200_PA) {
+    // mirrors the reference: B-bar has no PA gradient (src/mechanics_integrators.hpp:107-110)
+    delete c;
+    return fail("B-bar integration requires element assembly (EA)");
+  }
+  c->device = cfg->device;
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaSetDevice"); }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, c->device);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaGetDeviceProperties"); }
+  if (prop.major < 10) { delete c; return fail("exab200 kernels are built for sm_100a (Blackwell) only"); }
+  c->sm_count = prop.multiProcessorCount;
+  if (cfg->e2n) {
+    for (long i = 0; i < 8 * cfg->nelems; ++i)
+      if (cfg->e2n[i] < 0 || cfg->e2n[i] >= cfg->nnodes) { delete c; return fail("e2n entry out of range"); }
+    CK(cudaMalloc(&c->d_e2n, sizeof(int) * 8 * cfg->nelems));
+    CK(cudaMemcpy(c->d_e2n, cfg->e2n, sizeof(int) * 8 * cfg->nelems, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_ess, cfg->nnodes));
+    CK(cudaMemset(c->d_ess, 0, cfg->nnodes));
+  }
+  CK(cudaMalloc(&c->d_fail, sizeof(int)));
+  CK(cudaMemset(c->d_fail, 0, sizeof(int)));
+  if (cfg->assembly == EXAB200_EA) CK(cudaMalloc(&c->d_ea, sizeof(double) * 576 * cfg->nelems));
+  {
+    using SM = GradMultSmem<kEPT, kStages>;
+    CK(cudaFuncSetAttribute(k_grad_mult_pa<kEPT, kStages, LVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+    CK(cudaFuncSetAttribute(k_grad_mult_pa<kEPT, kStages, LVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+    CK(cudaFuncSetAttribute(k_grad_mult_pa<kEPT, kStages, EVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+  }
+  *out = c;
+  return 0;
+}
+
+void exab200_destroy(exab200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_e2n);
+  cudaFree(c->d_ess);
+  cudaFree(c->d_fail);
+  cudaFree(c->d_ea);
+  delete c;
+}
+
+int exab200_num_state_vars(const exab200_ctx* c) { return c ? c->mat.nhist : -1; }
+long exab200_launch_count(const exab200_ctx* c) { return c ? c->launches : -1; }
+int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm) {
+  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8) return fail("bad tuning");
+  c->ctas_per_sm = ctas_per_sm;
+  return 0;
+}
+
+int exab200_set_essential_mask(exab200_ctx* c, const unsigned char* h_mask) {
+  if (!c || !c->d_ess) return fail("context has no L-vector connectivity");
+  if (h_mask) {
+    CK(cudaMemcpy(c->d_ess, h_mask, c->cfg.nnodes, cudaMemcpyHostToDevice));
+    c->have_ess = false;
+    for (long i = 0; i < c->cfg.nnodes; ++i)
+      if (h_mask[i] & 7) { c->have_ess = true; break; }
+  } else {
+    CK(cudaMemset(c->d_ess, 0, c->cfg.nnodes));
+    c->have_ess = false;
+  }
+  return 0;
+}
+
+int exab200_hist_init(exab200_ctx* c, double* d_hist, void* stream) {
+  if (!c) return fail("null ctx");
+  const long npts = c->cfg.nelems * 8;
+  k_hist_init<<<(unsigned)((npts + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c->mat, d_hist, npts);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_setup_jacobians(exab200_ctx* c, const double* d_xbeg, const double* d_vel, double dt, double* d_jac,
+                            void* stream) {
+  NEED_L(c);
+  ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
+  k_jacobians<<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_xbeg, d_vel, dt, d_jac, io, c->cfg.nelems);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+static int model_setup_impl(exab200_ctx* c, int mode, double dt, const double* d_jac, const double* d_vel,
+                            const double* s0, const double* h0, double* s1, double* h1, double* mg, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!(dt > 0.0)) return fail("dt must be positive");
+  // the reference skips the tangent transpose for EA on a device backend (src/mechanics_ecmech.cpp:155)
+  // and then reads the row-major matrix as column-major; we always store d sigma_i/d eps_j at [j*6+i].
+  const int transpose = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned nb = eblocks(c->cfg.nelems, 128);
+  const long ne = c->cfg.nelems, nn = c->cfg.nnodes;
+  if (c->mat.nslip == 12) {
+    if (mode == LVEC)
+      k_model_setup<12, LVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+    else
+      k_model_setup<12, EVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+  } else {
+    if (mode == LVEC)
+      k_model_setup<24, LVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+    else
+      k_model_setup<24, EVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+  }
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_model_setup(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel_L, const double* s0,
+                        const double* h0, double* s1, double* h1, double* mg, void* stream) {
+  NEED_L(c);
+  return model_setup_impl(c, LVEC, dt, d_jac, d_vel_L, s0, h0, s1, h1, mg, stream);
+}
+int exab200_model_setup_evec(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel_E, const double* s0,
+                             const double* h0, double* s1, double* h1, double* mg, void* stream) {
+  return model_setup_impl(c, EVEC, dt, d_jac, d_vel_E, s0, h0, s1, h1, mg, stream);
+}
+
+int exab200_failed_points(exab200_ctx* c, void* stream, int* out) {
+  if (!c || !out) return fail("null argument");
+  CK(cudaMemcpyAsync(out, c->d_fail, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaMemsetAsync(c->d_fail, 0, sizeof(int), (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int exab200_residual_evec(exab200_ctx* c, const double* d_jac, const double* d_stress, double* d_y_E, void* stream) {
+  if (!c) return fail("null ctx");
+  ElemIO io{nullptr, nullptr, 0};
+  const unsigned nb = eblocks(c->cfg.nelems, 256);
+  if (c->cfg.integ == EXAB200_INTEG_BBAR)
+    k_residual<EVEC, true><<<nb, 256, 0, (cudaStream_t)stream>>>(d_stress, d_jac, d_y_E, io, c->cfg.nelems);
+  else
+    k_residual<EVEC, false><<<nb, 256, 0, (cudaStream_t)stream>>>(d_stress, d_jac, d_y_E, io, c->cfg.nelems);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_residual(exab200_ctx* c, const double* d_jac, const double* d_stress, double* d_y_L, void* stream) {
+  NEED_L(c);
+  CK(cudaMemsetAsync(d_y_L, 0, sizeof(double) * 3 * c->cfg.nnodes, (cudaStream_t)stream));
+  ElemIO io{c->d_e2n, c->have_ess ? c->d_ess : nullptr, c->cfg.nnodes};
+  const unsigned nb = eblocks(c->cfg.nelems, 256);
+  if (c->cfg.integ == EXAB200_INTEG_BBAR)
+    k_residual<LVEC, true><<<nb, 256, 0, (cudaStream_t)stream>>>(d_stress, d_jac, d_y_L, io, c->cfg.nelems);
+  else
+    k_residual<LVEC, false><<<nb, 256, 0, (cudaStream_t)stream>>>(d_stress, d_jac, d_y_L, io, c->cfg.nelems);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_ea_assemble(exab200_ctx* c, double dt, const double* d_matgrad, const double* d_jac, double* d_emat,
+                        void* stream) {
+  if (!c) return fail("null ctx");
+  const unsigned nb = eblocks(c->cfg.nelems, 128);
+  if (c->cfg.integ == EXAB200_INTEG_BBAR)
+    k_assemble_ea<true><<<nb, 128, 0, (cudaStream_t)stream>>>(d_matgrad, d_jac, d_emat, c->cfg.nelems, dt);
+  else
+    k_assemble_ea<false><<<nb, 128, 0, (cudaStream_t)stream>>>(d_matgrad, d_jac, d_emat, c->cfg.nelems, dt);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_grad_setup(exab200_ctx* c, double dt, const double* d_matgrad, const double* d_jac, void* stream) {
+  if (!c) return fail("null ctx");
+  c->grad_dt = dt;
+  c->d_matgrad = d_matgrad;
+  c->d_jac = d_jac;
+  if (c->cfg.assembly == EXAB200_EA) {
+    CK(cudaMemsetAsync(c->d_ea, 0, sizeof(double) * 576 * c->cfg.nelems, (cudaStream_t)stream));
+    return exab200_ea_assemble(c, dt, d_matgrad, d_jac, c->d_ea, stream);
+  }
+  return 0;
+}
+
+int exab200_grad_mult_evec(exab200_ctx* c, const double* d_x_E, double* d_y_E, void* stream) {
+  if (!c || !c->d_matgrad) return fail("grad_setup has not been called");
+  ElemIO io{nullptr, nullptr, 0};
+  if (c->cfg.assembly == EXAB200_EA) return exab200_ea_mult_evec(c, c->d_ea, d_x_E, d_y_E, stream);
+  return launch_grad_mult_pa<EVEC, false>(c, d_x_E, d_y_E, io, (cudaStream_t)stream);
+}
+
+int exab200_grad_mult(exab200_ctx* c, const double* d_x_L, double* d_y_L, int local_action, void* stream) {
+  NEED_L(c);
+  if (!c->d_matgrad) return fail("grad_setup has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_y_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
+  const bool ess = c->have_ess && !local_action;
+  ElemIO io{c->d_e2n, ess ? c->d_ess : nullptr, c->cfg.nnodes};
+  if (c->cfg.assembly == EXAB200_EA) {
+    k_ea_mult<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_x_L, d_y_L, io, c->cfg.nelems);
+    POST_LAUNCH(c);
+    return 0;
+  }
+  if (ess) return launch_grad_mult_pa<LVEC, true>(c, d_x_L, d_y_L, io, st);
+  return launch_grad_mult_pa<LVEC, false>(c, d_x_L, d_y_L, io, st);
+}
+
+int exab200_ea_mult_evec(exab200_ctx* c, const double* d_emat, const double* d_x_E, double* d_y_E, void* stream) {
+  if (!c) return fail("null ctx");
+  ElemIO io{nullptr, nullptr, 0};
+  k_ea_mult<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_emat, d_x_E, d_y_E, io, c->cfg.nelems);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_grad_diag_evec(exab200_ctx* c, double* d_diag_E, void* stream) {
+  if (!c || !c->d_matgrad) return fail("grad_setup has not been called");
+  ElemIO io{nullptr, nullptr, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->cfg.assembly == EXAB200_EA)
+    k_ea_diag<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_E, io, c->cfg.nelems);
+  else
+    k_grad_diag<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_E, io, c->cfg.nelems, c->grad_dt);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_grad_diag(exab200_ctx* c, double* d_diag_L, void* stream) {
+  NEED_L(c);
+  if (!c->d_matgrad) return fail("grad_setup has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_diag_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
+  ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
+  if (c->cfg.assembly == EXAB200_EA)
+    k_ea_diag<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_L, io, c->cfg.nelems);
+  else
+    k_grad_diag<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
+  POST_LAUNCH(c);
+  if (c->have_ess) {
+    k_set_ess_one<<<(unsigned)((c->cfg.nnodes + 255) / 256), 256, 0, st>>>(d_diag_L, c->d_ess, c->cfg.nnodes);
+    POST_LAUNCH(c);
+  }
+  return 0;
+}
+
+int exab200_vol_sum(exab200_ctx* c, const double* d_jac, const double* d_qf, int vdim, double* d_out, void* stream) {
+  if (!c) return fail("null ctx");
+  if (vdim < 1 || vdim > 40) return fail("vdim out of range (1..40)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (vdim + 1), st));
+  const long npts = c->cfg.nelems * 8;
+  long nb = (npts + 255) / 256;
+  if (nb > (long)c->sm_count * 8) nb = (long)c->sm_count * 8;
+  if (vdim <= 9)
+    k_vol_sum<9><<<(unsigned)nb, 256, 0, st>>>(d_qf, d_jac, vdim, npts, d_out);
+  else
+    k_vol_sum<40><<<(unsigned)nb, 256, 0, st>>>(d_qf, d_jac, vdim, npts, d_out);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_calc_dp(exab200_ctx* c, const double* d_hist, double* d_dp, void* stream) {
+  if (!c) return fail("null ctx");
+  const long npts = c->cfg.nelems * 8;
+  k_calc_dp<<<(unsigned)((npts + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c->mat, d_hist, d_dp, npts);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+int exab200_grad_calc(exab200_ctx* c, const double* d_jac, const double* d_field_L, double* d_grad, void* stream) {
+  NEED_L(c);
+  ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
+  k_grad_calc<<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_jac, d_field_L, d_grad, io, c->cfg.nelems);
+  POST_LAUNCH(c);
+  return 0;
+}
+
+}  // extern "C"

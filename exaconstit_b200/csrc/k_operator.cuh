@@ -1,0 +1,634 @@
+// Element kernels of the matrix-free operator path (sm_100a, fp64, no tensor cores: 3x3 / 6x6
+// tensor algebra).  Reference behaviour each kernel replaces is cited at its definition
+// (paths relative to the ExaConstit source tree).
+#pragma once
+#include "exab200_common.cuh"
+
+namespace exab {
+
+// How an element kernel reaches the nodal vectors.
+//   LVEC: x/y are L-vectors (byNODES: comp*nnodes + node); gather through e2n, scatter with
+//         red.global.add.f64; essential dofs masked on the fly (bit i of essmask[node]).
+//   EVEC: x/y are E-vectors X(a,i,e) = x[e*24 + i*8 + a_native] exactly as the reference's
+//         integrator virtuals receive them (src/mechanics_integrators.cpp:580-581).
+enum VecMode { LVEC = 0, EVEC = 1 };
+
+struct ElemIO {
+  const int* __restrict__ e2n;               // 8*nelems, NATIVE order (LVEC)
+  const unsigned char* __restrict__ essmask;  // nnodes or nullptr (LVEC)
+  long nnodes;
+};
+
+// ------------------------------------------------------------------------------------------
+// K2: gradient (tangent-stiffness) operator apply, y += K x, matrix-free from the 6x6 material
+// tangent and the Jacobians.  Replaces, in one launch:
+//   ExaModel::TransformMatGradTo4D            src/mechanics_model.cpp:949-1061
+//   ExaNLFIntegrator::AssembleGradPA          src/mechanics_integrators.cpp:331-513
+//   ExaNLFIntegrator::AddMultGradPA           src/mechanics_integrators.cpp:562-622
+//   and in LVEC mode also ElementRestriction Mult/MultTranspose and the essential-dof masking of
+//   PANonlinearMechOperatorGradExt::TMult     src/mechanics_operator_ext.cpp:136-174
+// y_{a,k} = sum_q dt W_q detJ (dN_a/dx_p) C(p,k,l,m) (dv_l/dx_m), C(p,k,l,m) = K(v(p,k), v(l,m)).
+//
+// Persistent CTAs; each stage holds one tile of EPT elements: matGrad (36 dbl/qpt) and J
+// (9 dbl/qpt) are streamed HBM -> shared memory with cp.async.bulk (TMA 1-D) completing on an
+// mbarrier, STAGES deep, so >= (STAGES-1) * EPT * 2880 B are in flight per SM while the current
+// tile is contracted out of shared memory.  The two 1152-B halves of an element's matGrad block
+// are skewed by 16 B in shared memory so that the per-lane LDS.128 stream is bank-conflict free.
+// ------------------------------------------------------------------------------------------
+constexpr int kCHalfBytes = 4 * 36 * 8;           // 1152: four quadrature points of matGrad
+constexpr int kCElemSmem = 2 * kCHalfBytes + 16;  // 2320: skewed element block
+constexpr int kJElemBytes = 8 * 9 * 8;            // 576
+
+template <int EPT, int STAGES>
+struct GradMultSmem {
+  alignas(16) unsigned char c[STAGES][EPT * kCElemSmem];
+  alignas(16) unsigned char j[STAGES][EPT * kJElemBytes];
+  alignas(8) uint64_t full[STAGES];
+};
+
+template <int EPT, int STAGES, int MODE, bool ESS>
+__global__ void __launch_bounds__(EPT * 8) k_grad_mult_pa(const double* __restrict__ matgrad,
+                                                          const double* __restrict__ jac,
+                                                          const double* __restrict__ x, double* __restrict__ y,
+                                                          ElemIO io, long nelems, double dt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GradMultSmem<EPT, STAGES>& sm = *reinterpret_cast<GradMultSmem<EPT, STAGES>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 7;          // node / quadrature point (lexicographic) inside the element
+  const int el = tid >> 3;           // element slot inside the tile
+  const long ntiles = (nelems + EPT - 1) / EPT;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // producer: warp 0, one lane per element of the tile
+  auto issue = [&](long tile, int s) {
+    if (tid < 32) {
+      const long e0 = tile * EPT;
+      const int ne = (int)min((long)EPT, nelems - e0);
+      if (tid == 0) mbar_arrive_expect_tx(&sm.full[s], (uint32_t)ne * (2 * kCHalfBytes + kJElemBytes));
+      __syncwarp();
+      for (int i = tid; i < ne; i += 32) {
+        const unsigned char* gc = reinterpret_cast<const unsigned char*>(matgrad + (e0 + i) * 288);
+        unsigned char* sc = &sm.c[s][i * kCElemSmem];
+        bulk_g2s(sc, gc, kCHalfBytes, &sm.full[s]);
+        bulk_g2s(sc + kCHalfBytes + 16, gc + kCHalfBytes, kCHalfBytes, &sm.full[s]);
+        bulk_g2s(&sm.j[s][i * kJElemBytes], jac + (e0 + i) * 72, kJElemBytes, &sm.full[s]);
+      }
+    }
+  };
+
+  // prologue: fill the ring
+  {
+    long t = blockIdx.x;
+    for (int s = 0; s < STAGES; ++s, t += gridDim.x)
+      if (t < ntiles) issue(t, s);
+  }
+
+  // register-prefetched nodal data of the next tile (hides the e2n -> x dependent loads)
+  auto load_nodal = [&](long tile, long& nid, unsigned& msk, double& x0, double& x1, double& x2) {
+    const long e = tile * EPT + el;
+    nid = -1; msk = 0; x0 = x1 = x2 = 0.0;
+    if (tile < ntiles && e < nelems) {
+      if (MODE == LVEC) {
+        nid = io.e2n[e * 8 + lex_to_native(lane)];
+        if (ESS) msk = io.essmask[nid];
+        x0 = (msk & 1) ? 0.0 : x[nid];
+        x1 = (msk & 2) ? 0.0 : x[io.nnodes + nid];
+        x2 = (msk & 4) ? 0.0 : x[2 * io.nnodes + nid];
+      } else {
+        nid = e * 24 + lex_to_native(lane);
+        x0 = x[nid]; x1 = x[nid + 8]; x2 = x[nid + 16];
+      }
+    }
+  };
+
+  long nid_n; unsigned msk_n; double xn0, xn1, xn2;
+  load_nodal(blockIdx.x, nid_n, msk_n, xn0, xn1, xn2);
+
+  int s = 0;
+  uint32_t phase = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long nid = nid_n; const unsigned msk = msk_n;
+    const double u0 = xn0, u1 = xn1, u2 = xn2;
+    load_nodal(tile + gridDim.x, nid_n, msk_n, xn0, xn1, xn2);
+
+    // reference-space velocity gradient at this lane's quadrature point: d(i,s) = dv_i/dxi_s
+    double d00, d01, d02, d10, d11, d12, d20, d21, d22;
+    nodal_to_qp_grad(u0, lane, d00, d01, d02);
+    nodal_to_qp_grad(u1, lane, d10, d11, d12);
+    nodal_to_qp_grad(u2, lane, d20, d21, d22);
+
+    mbar_wait(&sm.full[s], phase);
+
+    const long e = tile * EPT + el;
+    const bool active = e < nelems;
+    double t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0, t20 = 0, t21 = 0, t22 = 0;  // T(j,k)
+    if (active) {
+      const double* Jq = reinterpret_cast<const double*>(&sm.j[s][el * kJElemBytes]) + lane * 9;
+      double J[9], adj[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+      const double det = adjugate(J, adj);
+      const double c = dt * kWq / det;
+      // det * dv_i/dx_t = sum_s d(i,s) adj(s,t)
+      const double g00 = d00 * adj[0] + d01 * adj[3] + d02 * adj[6];
+      const double g01 = d00 * adj[1] + d01 * adj[4] + d02 * adj[7];
+      const double g02 = d00 * adj[2] + d01 * adj[5] + d02 * adj[8];
+      const double g10 = d10 * adj[0] + d11 * adj[3] + d12 * adj[6];
+      const double g11 = d10 * adj[1] + d11 * adj[4] + d12 * adj[7];
+      const double g12 = d10 * adj[2] + d11 * adj[5] + d12 * adj[8];
+      const double g20 = d20 * adj[0] + d21 * adj[3] + d22 * adj[6];
+      const double g21 = d20 * adj[1] + d21 * adj[4] + d22 * adj[7];
+      const double g22 = d20 * adj[2] + d21 * adj[5] + d22 * adj[8];
+      // Voigt strain-rate-like vector (engineering shear), scaled by dt W / det
+      const double eps[6] = {c * g00, c * g11, c * g22, c * (g12 + g21), c * (g02 + g20), c * (g01 + g10)};
+      // S_I = sum_J K(I,J) eps_J, K(I,J) at [J*6 + I]; stream the 36 doubles in memory order
+      const unsigned char* cb = &sm.c[s][el * kCElemSmem + (lane >> 2) * (kCHalfBytes + 16) + (lane & 3) * 288];
+      const double2* C2 = reinterpret_cast<const double2*>(cb);
+      double S[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int Jc = 0; Jc < 6; ++Jc) {
+        const double2 a = C2[Jc * 3 + 0], b = C2[Jc * 3 + 1], cc = C2[Jc * 3 + 2];
+        S[0] += a.x * eps[Jc]; S[1] += a.y * eps[Jc];
+        S[2] += b.x * eps[Jc]; S[3] += b.y * eps[Jc];
+        S[4] += cc.x * eps[Jc]; S[5] += cc.y * eps[Jc];
+      }
+      // T(j,k) = sum_p adj(j,p) S(p,k); S symmetric 3x3 from Voigt (0,1,2,3=yz,4=xz,5=xy)
+      t00 = adj[0] * S[0] + adj[1] * S[5] + adj[2] * S[4];
+      t01 = adj[0] * S[5] + adj[1] * S[1] + adj[2] * S[3];
+      t02 = adj[0] * S[4] + adj[1] * S[3] + adj[2] * S[2];
+      t10 = adj[3] * S[0] + adj[4] * S[5] + adj[5] * S[4];
+      t11 = adj[3] * S[5] + adj[4] * S[1] + adj[5] * S[3];
+      t12 = adj[3] * S[4] + adj[4] * S[3] + adj[5] * S[2];
+      t20 = adj[6] * S[0] + adj[7] * S[5] + adj[8] * S[4];
+      t21 = adj[6] * S[5] + adj[7] * S[1] + adj[8] * S[3];
+      t22 = adj[6] * S[4] + adj[7] * S[3] + adj[8] * S[2];
+    }
+    // all lanes of the warp take part in the butterflies
+    const double y0 = qp_grad_to_nodal(t00, t10, t20, lane);
+    const double y1 = qp_grad_to_nodal(t01, t11, t21, lane);
+    const double y2 = qp_grad_to_nodal(t02, t12, t22, lane);
+    if (active) {
+      if (MODE == LVEC) {
+        if (!(msk & 1)) red_add_f64(&y[nid], y0);
+        if (!(msk & 2)) red_add_f64(&y[io.nnodes + nid], y1);
+        if (!(msk & 4)) red_add_f64(&y[2 * io.nnodes + nid], y2);
+      } else {
+        y[nid] += y0; y[nid + 8] += y1; y[nid + 16] += y2;
+      }
+    }
+    // release the stage and refill it with the tile STAGES grid-strides ahead
+    __syncthreads();
+    const long tnext = tile + (long)STAGES * gridDim.x;
+    if (tnext < ntiles) issue(tnext, s);
+    if (++s == STAGES) { s = 0; phase ^= 1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Residual action: y_{a,k} += sum_q W_q [adj(J) sigma](j,k) G(a,j,q)
+// Replaces ExaNLFIntegrator::AssemblePA (three passes, src/mechanics_integrators.cpp:160-314)
+// + AddMultPA (:518-557) [+ restriction^T and essential-dof zeroing of MultVec,
+// src/mechanics_operator_ext.cpp:176-202].  BBAR selects ICExaNLFIntegrator::AddMultPA
+// (:1961-2088) with the element-average shape gradients computed in-kernel (:1895-1952).
+// One thread per quadrature point, 8 lanes per element; plain coalescable global loads (this
+// kernel runs once per Newton residual, not in the PCG loop).
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool BBAR>
+__global__ void __launch_bounds__(256) k_residual(const double* __restrict__ stress, const double* __restrict__ jac,
+                                                  double* __restrict__ y, ElemIO io, long nelems) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;
+  const long e = gt >> 3;
+  const bool active = e < nelems;
+  double J[9], adj[9], S[6], det = 1.0;
+  if (active) {
+    const double* Jq = jac + (e * 8 + lane) * 9;
+    const double* Sq = stress + (e * 8 + lane) * 6;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) S[i] = Sq[i];
+    det = adjugate(J, adj);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) adj[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) S[i] = 0.0;
+  }
+  double y0, y1, y2;
+  if (!BBAR) {
+    const double w = active ? kWq : 0.0;
+    const double t00 = w * (adj[0] * S[0] + adj[1] * S[5] + adj[2] * S[4]);
+    const double t01 = w * (adj[0] * S[5] + adj[1] * S[1] + adj[2] * S[3]);
+    const double t02 = w * (adj[0] * S[4] + adj[1] * S[3] + adj[2] * S[2]);
+    const double t10 = w * (adj[3] * S[0] + adj[4] * S[5] + adj[5] * S[4]);
+    const double t11 = w * (adj[3] * S[5] + adj[4] * S[1] + adj[5] * S[3]);
+    const double t12 = w * (adj[3] * S[4] + adj[4] * S[3] + adj[5] * S[2]);
+    const double t20 = w * (adj[6] * S[0] + adj[7] * S[5] + adj[8] * S[4]);
+    const double t21 = w * (adj[6] * S[5] + adj[7] * S[1] + adj[8] * S[3]);
+    const double t22 = w * (adj[6] * S[4] + adj[7] * S[3] + adj[8] * S[2]);
+    y0 = qp_grad_to_nodal(t00, t10, t20, lane);
+    y1 = qp_grad_to_nodal(t01, t11, t21, lane);
+    y2 = qp_grad_to_nodal(t02, t12, t22, lane);
+  } else {
+    // B-bar: y_{a,I} = sum_q W detJ [ b_p(a,q) dev-part + eDS_I(a) * mean-part ]
+    //   Bbar^T sigma = b_p s_{pI} + (1/3)(eDS_I - b_I) tr(sigma)
+    // => sum_q W detJ b_p (s_{pI} - tr/3 delta_{pI})   (plain operator on the deviatoric-shifted stress)
+    //    + eDS_I(a) * sum_q W detJ tr(sigma)/3
+    const double w = active ? kWq : 0.0;
+    const double tr3 = (S[0] + S[1] + S[2]) * (1.0 / 3.0);
+    const double D0 = S[0] - tr3, D1 = S[1] - tr3, D2 = S[2] - tr3;
+    const double t00 = w * (adj[0] * D0 + adj[1] * S[5] + adj[2] * S[4]);
+    const double t01 = w * (adj[0] * S[5] + adj[1] * D1 + adj[2] * S[3]);
+    const double t02 = w * (adj[0] * S[4] + adj[1] * S[3] + adj[2] * D2);
+    const double t10 = w * (adj[3] * D0 + adj[4] * S[5] + adj[5] * S[4]);
+    const double t11 = w * (adj[3] * S[5] + adj[4] * D1 + adj[5] * S[3]);
+    const double t12 = w * (adj[3] * S[4] + adj[4] * S[3] + adj[5] * D2);
+    const double t20 = w * (adj[6] * D0 + adj[7] * S[5] + adj[8] * S[4]);
+    const double t21 = w * (adj[6] * S[5] + adj[7] * D1 + adj[8] * S[3]);
+    const double t22 = w * (adj[6] * S[4] + adj[7] * S[3] + adj[8] * D2);
+    y0 = qp_grad_to_nodal(t00, t10, t20, lane);
+    y1 = qp_grad_to_nodal(t01, t11, t21, lane);
+    y2 = qp_grad_to_nodal(t02, t12, t22, lane);
+    // element sums: volume, mean-stress moment, and eDS numerators sum_q W b_c(a,q)
+    double vol = w * det, pm = w * det * tr3;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) { vol += shfl_xor_d(vol, m); pm += shfl_xor_d(pm, m); }
+    const double e0 = qp_grad_to_nodal(w * adj[0], w * adj[3], w * adj[6], lane);
+    const double e1 = qp_grad_to_nodal(w * adj[1], w * adj[4], w * adj[7], lane);
+    const double e2 = qp_grad_to_nodal(w * adj[2], w * adj[5], w * adj[8], lane);
+    const double f = active ? pm / vol : 0.0;
+    y0 += e0 * f; y1 += e1 * f; y2 += e2 * f;
+  }
+  if (active) {
+    if (MODE == LVEC) {
+      const long nid = io.e2n[e * 8 + lex_to_native(lane)];
+      const unsigned msk = io.essmask ? io.essmask[nid] : 0u;
+      if (!(msk & 1)) red_add_f64(&y[nid], y0);
+      if (!(msk & 2)) red_add_f64(&y[io.nnodes + nid], y1);
+      if (!(msk & 4)) red_add_f64(&y[2 * io.nnodes + nid], y2);
+    } else {
+      const long o = e * 24 + lex_to_native(lane);
+      y[o] += y0; y[o + 8] += y1; y[o + 16] += y2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagonal of the gradient operator.  Replaces ExaNLFIntegrator::AssembleGradDiagonalPA
+// (src/mechanics_integrators.cpp:625-748) [+ restriction^T, src/mechanics_operator_ext.cpp:95-123].
+// lane = quadrature point; the 24 per-point partials are summed over the element with a
+// reduce-scatter butterfly (12 + 6 + 3 doubles), leaving node `lane`'s 3 entries in each lane.
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ matgrad, const double* __restrict__ jac,
+                                                   double* __restrict__ diag, ElemIO io, long nelems, double dt) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;
+  const long e = gt >> 3;
+  const bool active = e < nelems;
+  double v[8][3];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) v[a][0] = v[a][1] = v[a][2] = 0.0;
+  if (active) {
+    double J[9], adj[9], K[36];
+    const double* Jq = jac + (e * 8 + lane) * 9;
+    const double* Kq = matgrad + (e * 8 + lane) * 36;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) K[i] = Kq[i];
+    const double det = adjugate(J, adj);
+    const double c = dt * kWq / det;
+    const int vg[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      double g[3], b[3];
+      shape_grad(a, lane, g);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) b[cc] = g[0] * adj[cc] + g[1] * adj[3 + cc] + g[2] * adj[6 + cc];
+#pragma unroll
+      for (int I = 0; I < 3; ++I) {
+        double s = 0.0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          double w = 0.0;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) w += b[r] * K[vg[I][r] * 6 + vg[I][p]];
+          s += b[p] * w;
+        }
+        v[a][I] = c * s;
+      }
+    }
+  }
+  // reduce-scatter over the 8 lanes: after the three stages lane l holds sum_q v_q[l][:]
+  double w4[4][3];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int I = 0; I < 3; ++I) {
+      const bool hi = lane & 4;
+      const double send = hi ? v[a][I] : v[a + 4][I];
+      const double keep = hi ? v[a + 4][I] : v[a][I];
+      w4[a][I] = keep + shfl_xor_d(send, 4);
+    }
+  double w2[2][3];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int I = 0; I < 3; ++I) {
+      const bool hi = lane & 2;
+      const double send = hi ? w4[a][I] : w4[a + 2][I];
+      const double keep = hi ? w4[a + 2][I] : w4[a][I];
+      w2[a][I] = keep + shfl_xor_d(send, 2);
+    }
+  double w1[3];
+#pragma unroll
+  for (int I = 0; I < 3; ++I) {
+    const bool hi = lane & 1;
+    const double send = hi ? w2[0][I] : w2[1][I];
+    const double keep = hi ? w2[1][I] : w2[0][I];
+    w1[I] = keep + shfl_xor_d(send, 1);
+  }
+  if (active) {
+    if (MODE == LVEC) {
+      const long nid = io.e2n[e * 8 + lex_to_native(lane)];
+      red_add_f64(&diag[nid], w1[0]);
+      red_add_f64(&diag[io.nnodes + nid], w1[1]);
+      red_add_f64(&diag[2 * io.nnodes + nid], w1[2]);
+    } else {
+      const long o = e * 24 + lex_to_native(lane);
+      diag[o] += w1[0]; diag[o + 8] += w1[1]; diag[o + 16] += w1[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Jacobians at the quadrature points from nodal coordinates: J(i,s,q,e) = dx_i/dxi_s.
+// Replaces mesh->DeleteGeometricFactors()/GetGeometricFactors(JACOBIANS) + the transposing copy
+// of NonlinearMechOperator::SetupJacobianTerms (src/mechanics_operator.cpp:350-391); with
+// vel != nullptr the coordinates are x_beg + dt*vel, i.e. ExaModel::UpdateEndCoords
+// (src/mechanics_model.cpp:445-481) fused in.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_jacobians(const double* __restrict__ xbeg, const double* __restrict__ vel,
+                                                   double dt, double* __restrict__ jac, ElemIO io, long nelems) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;
+  const long e = gt >> 3;
+  const bool active = e < nelems;
+  double c0 = 0, c1 = 0, c2 = 0;
+  if (active) {
+    const long nid = io.e2n[e * 8 + lex_to_native(lane)];
+    c0 = xbeg[nid]; c1 = xbeg[io.nnodes + nid]; c2 = xbeg[2 * io.nnodes + nid];
+    if (vel) { c0 += dt * vel[nid]; c1 += dt * vel[io.nnodes + nid]; c2 += dt * vel[2 * io.nnodes + nid]; }
+  }
+  double J[9];
+  nodal_to_qp_grad(c0, lane, J[0], J[3], J[6]);
+  nodal_to_qp_grad(c1, lane, J[1], J[4], J[7]);
+  nodal_to_qp_grad(c2, lane, J[2], J[5], J[8]);
+  if (active) {
+    double* o = jac + (e * 8 + lane) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = J[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Element-matrix assembly (24x24 per element).  Replaces ExaNLFIntegrator::AssembleEA
+// (src/mechanics_integrators.cpp:756-1017) and, with BBAR, ICExaNLFIntegrator::AssembleEA
+// (:1195-1604; eDS from :1895-1952 computed in-kernel).
+//   E(l+8I, k+8Kc, e) = sum_q c_q sum_{R,S} B_l(R,I) K(R,S) B_k(S,Kc),  memory [e*576 + col*24 + row]
+// lane = column node k; it loops the element's 8 points and keeps its 24x3 column block in
+// registers; rows/cols are in NATIVE node order like the reference.
+// ------------------------------------------------------------------------------------------
+template <bool BBAR>
+__global__ void __launch_bounds__(128) k_assemble_ea(const double* __restrict__ matgrad, const double* __restrict__ jac,
+                                                     double* __restrict__ ea, long nelems, double dt) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;  // lexicographic column node
+  const long e = gt >> 3;
+  if (e >= nelems) return;  // no shuffles in this kernel
+  double acc[8][3][3];
+#pragma unroll
+  for (int l = 0; l < 8; ++l)
+#pragma unroll
+    for (int I = 0; I < 3; ++I) acc[l][I][0] = acc[l][I][1] = acc[l][I][2] = 0.0;
+  // B-bar: element-average physical gradients eDS(a,c) and volume
+  double eds[8][3];
+  if (BBAR) {
+    double vol = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) eds[a][0] = eds[a][1] = eds[a][2] = 0.0;
+    for (int q = 0; q < 8; ++q) {
+      double J[9], adj[9];
+      const double* Jq = jac + (e * 8 + q) * 9;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+      vol += kWq * adjugate(J, adj);
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        double g[3];
+        shape_grad(a, q, g);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) eds[a][cc] += kWq * (g[0] * adj[cc] + g[1] * adj[3 + cc] + g[2] * adj[6 + cc]);
+      }
+    }
+    const double iv = 1.0 / vol;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) { eds[a][0] *= iv; eds[a][1] *= iv; eds[a][2] *= iv; }
+  }
+  for (int q = 0; q < 8; ++q) {
+    double J[9], adj[9], K[36];
+    const double* Jq = jac + (e * 8 + q) * 9;
+    const double* Kq = matgrad + (e * 8 + q) * 36;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) K[i] = Kq[i];
+    const double det = adjugate(J, adj);
+    const double idet = 1.0 / det;
+    const double c = dt * kWq * det;  // on true physical gradients
+    auto bmat = [&](int a, double B[6][3]) {
+      double g[3], b[3];
+      shape_grad(a, q, g);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) b[cc] = idet * (g[0] * adj[cc] + g[1] * adj[3 + cc] + g[2] * adj[6 + cc]);
+      double m0 = 0, m1 = 0, m2 = 0;
+      if (BBAR) {
+        m0 = (eds[a][0] - b[0]) * (1.0 / 3.0);
+        m1 = (eds[a][1] - b[1]) * (1.0 / 3.0);
+        m2 = (eds[a][2] - b[2]) * (1.0 / 3.0);
+      }
+      B[0][0] = m0 + b[0]; B[0][1] = m1;        B[0][2] = m2;
+      B[1][0] = m0;        B[1][1] = m1 + b[1]; B[1][2] = m2;
+      B[2][0] = m0;        B[2][1] = m1;        B[2][2] = m2 + b[2];
+      B[3][0] = 0.0;       B[3][1] = b[2];      B[3][2] = b[1];
+      B[4][0] = b[2];      B[4][1] = 0.0;       B[4][2] = b[0];
+      B[5][0] = b[1];      B[5][1] = b[0];      B[5][2] = 0.0;
+    };
+    double Bk[6][3], KB[6][3];
+    bmat(lane, Bk);
+#pragma unroll
+    for (int R = 0; R < 6; ++R)
+#pragma unroll
+      for (int Kc = 0; Kc < 3; ++Kc) {
+        double s = 0.0;
+#pragma unroll
+        for (int S = 0; S < 6; ++S) s += K[S * 6 + R] * Bk[S][Kc];
+        KB[R][Kc] = c * s;
+      }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      double Bl[6][3];
+      bmat(l, Bl);
+#pragma unroll
+      for (int I = 0; I < 3; ++I)
+#pragma unroll
+        for (int Kc = 0; Kc < 3; ++Kc) {
+          double s = 0.0;
+#pragma unroll
+          for (int R = 0; R < 6; ++R) s += Bl[R][I] * KB[R][Kc];
+          acc[l][I][Kc] += s;
+        }
+    }
+  }
+  const int kn = lex_to_native(lane);
+#pragma unroll
+  for (int Kc = 0; Kc < 3; ++Kc) {
+    double* col = ea + e * 576 + (long)(kn + 8 * Kc) * 24;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const int ln = lex_to_native(l);
+#pragma unroll
+      for (int I = 0; I < 3; ++I) col[ln + 8 * I] += acc[l][I][Kc];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Element-matrix apply: Y(j,e) += sum_i E(i,j,e) X(i,e) (the reference applies the stored matrix
+// transposed, src/mechanics_operator_ext.cpp:303-314).  lane = node; it owns columns
+// j = lane_native + 8*comp.  LVEC fuses restriction, restriction^T and essential-dof masking
+// (EANonlinearMechOperatorGradExt::TMult, :278-328).
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, const double* __restrict__ x,
+                                                 double* __restrict__ y, ElemIO io, long nelems) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;
+  const long e = gt >> 3;
+  const bool active = e < nelems;
+  const int an = lex_to_native(lane);
+  long nid = 0; unsigned msk = 0;
+  double u0 = 0, u1 = 0, u2 = 0;
+  if (active) {
+    if (MODE == LVEC) {
+      nid = io.e2n[e * 8 + an];
+      msk = io.essmask ? io.essmask[nid] : 0u;
+      u0 = (msk & 1) ? 0.0 : x[nid];
+      u1 = (msk & 2) ? 0.0 : x[io.nnodes + nid];
+      u2 = (msk & 4) ? 0.0 : x[2 * io.nnodes + nid];
+    } else {
+      nid = e * 24 + an;
+      u0 = x[nid]; u1 = x[nid + 8]; u2 = x[nid + 16];
+    }
+  }
+  // all 24 element dofs to every lane: xe[i] with i = a_native + 8*comp
+  double xe[24];
+  const int base = (threadIdx.x & 31) & ~7;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int src = base + lex_to_native(a);  // lane holding native node a (lex_to_native is an involution)
+    xe[a] = __shfl_sync(kFull, u0, src);
+    xe[a + 8] = __shfl_sync(kFull, u1, src);
+    xe[a + 16] = __shfl_sync(kFull, u2, src);
+  }
+  if (!active) return;
+  double r[3];
+#pragma unroll
+  for (int cmp = 0; cmp < 3; ++cmp) {
+    const double2* col = reinterpret_cast<const double2*>(ea + e * 576 + (long)(an + 8 * cmp) * 24);
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const double2 m = col[i];
+      s0 += m.x * xe[2 * i];
+      s1 += m.y * xe[2 * i + 1];
+    }
+    r[cmp] = s0 + s1;
+  }
+  if (MODE == LVEC) {
+    if (!(msk & 1)) red_add_f64(&y[nid], r[0]);
+    if (!(msk & 2)) red_add_f64(&y[io.nnodes + nid], r[1]);
+    if (!(msk & 4)) red_add_f64(&y[2 * io.nnodes + nid], r[2]);
+  } else {
+    y[nid] += r[0]; y[nid + 8] += r[1]; y[nid + 16] += r[2];
+  }
+}
+
+// EA AssembleDiagonal (src/mechanics_operator_ext.cpp:228-265): diag of the element matrices.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ea_diag(const double* __restrict__ ea, double* __restrict__ diag, ElemIO io,
+                                                 long nelems) {
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 7;
+  const long e = gt >> 3;
+  if (e >= nelems) return;
+  const int an = lex_to_native(lane);
+#pragma unroll
+  for (int cmp = 0; cmp < 3; ++cmp) {
+    const int j = an + 8 * cmp;
+    const double v = ea[e * 576 + (long)j * 24 + j];
+    if (MODE == LVEC) red_add_f64(&diag[cmp * io.nnodes + io.e2n[e * 8 + an]], v);
+    else diag[e * 24 + j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Volume-weighted sums of a quadrature function: out[c] = sum w f_c (c < vdim), out[vdim] = sum w,
+// w = detJ W.  One pass over the data (the reference makes `vdim` passes,
+// src/mechanics_kernels.hpp:51-133).  out must be zeroed; block partials are combined with
+// one red.add per component per block.
+// ------------------------------------------------------------------------------------------
+template <int VDIM_MAX>
+__global__ void __launch_bounds__(256) k_vol_sum(const double* __restrict__ qf, const double* __restrict__ jac, int vdim,
+                                                 long npts, double* __restrict__ out) {
+  __shared__ double red[8][VDIM_MAX + 1];
+  double acc[VDIM_MAX + 1];
+#pragma unroll
+  for (int c = 0; c <= VDIM_MAX; ++c) acc[c] = 0.0;
+  for (long p = (long)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += (long)gridDim.x * blockDim.x) {
+    double J[9], adj[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = jac[p * 9 + i];
+    const double w = adjugate(J, adj) * kWq;
+    acc[VDIM_MAX] += w;
+#pragma unroll
+    for (int c = 0; c < VDIM_MAX; ++c)
+      if (c < vdim) acc[c] += w * qf[p * vdim + c];
+  }
+#pragma unroll
+  for (int c = 0; c <= VDIM_MAX; ++c) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc[c] += __shfl_xor_sync(kFull, acc[c], m);
+  }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int c = 0; c <= VDIM_MAX; ++c) red[warp][c] = acc[c];
+  __syncthreads();
+  if (threadIdx.x <= VDIM_MAX) {
+    const int c = threadIdx.x;
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][c];
+    if (c < vdim) red_add_f64(&out[c], s);
+    else if (c == VDIM_MAX) red_add_f64(&out[vdim], s);
+  }
+}
+
+}  // namespace exab

@@ -1,0 +1,53 @@
+"""The reference's regression cases (test/data/*.toml) restated as oracle/product inputs."""
+import os
+
+import numpy as np
+
+_G = None
+
+
+def goldens():
+    global _G
+    if _G is None:
+        _G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exaconstit_goldens.npz"))
+    return _G
+
+
+def refined_grain_ids(n_coarse=5):
+    """test/data/voce_pa.toml:122,131-137: 5x5x5 auto mesh, ref_ser=1 -> 10^3 hexes; children inherit
+    the parent's grain attribute (src/mechanics_driver.cpp:276-281,308-310); grains.txt is x-fastest."""
+    g = goldens()["grains"].reshape(n_coarse, n_coarse, n_coarse)  # [z][y][x]
+    fine = np.repeat(np.repeat(np.repeat(g, 2, axis=0), 2, axis=1), 2, axis=2)
+    return fine.ravel().astype(np.int32)
+
+
+# uniaxial symmetric BCs of test/data/voce_pa.toml:40-51
+def uniaxial_bcs(rate=0.001):
+    return [(1, [1, 2, 3, 4], [3, 1, 2, 3], [[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, rate]])]
+
+
+CASES = {
+    # name: (xtal, kin, props key, assembly, nr, kr, golden key)
+    "voce_pa": (0, 0, "props_cp_voce", 0, (5e-5, 5e-10, 25), (1e-7, 1e-27, 1000), "voce_pa_stress"),
+    "voce_ea": (0, 0, "props_cp_voce", 1, (5e-5, 5e-10, 25), (1e-7, 1e-27, 1000), "voce_ea_stress"),
+    "voce_full": (0, 0, "props_cp_voce", 0, (5e-5, 5e-10, 25), (1e-7, 1e-27, 1000), "voce_full_stress"),
+    "voce_nl_full": (0, 1, "props_cp_vocenl", 0, (5e-5, 5e-10, 25), (1e-7, 1e-27, 1000), "voce_full_stress"),
+    "voce_bcc": (1, 0, "props_cp_voce", 0, (5e-5, 5e-10, 25), (1e-7, 1e-27, 1000), "voce_bcc_stress"),
+    "mtsdd_bcc": (1, 2, "props_cp_mts", 0, (1e-5, 1e-12, 25), (1e-7, 1e-27, 250), "mtsdd_bcc_stress"),
+    "mtsdd_full": (0, 2, "props_cp_mts", 0, (1e-5, 1e-12, 25), (1e-7, 1e-27, 250), "mtsdd_full_stress"),
+}
+
+
+def case_inputs(name):
+    g = goldens()
+    xtal, kin, pk, assembly, nr, kr, gk = CASES[name]
+    return dict(n=(10, 10, 10), length=(1.0, 1.0, 1.0), xtal=xtal, kin=kin, props=g[pk], temp_k=298.0,
+                grain_ids=refined_grain_ids(), quats=g["voce_quats"], dts=g["custom_dt"], bcs=uniaxial_bcs(),
+                assembly=assembly, nr=nr, kr=kr), g[gk]
+
+
+def golden_rel_err(sim_stress, gold):
+    """Error measure in units of the 6th significant digit of the golden's loaded component."""
+    s = np.asarray(sim_stress)[: gold.shape[0]]
+    scale = np.abs(gold[:, 2:3])
+    return np.abs(s - gold) / scale

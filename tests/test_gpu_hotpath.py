@@ -1,0 +1,142 @@
+"""GPU parity tests: the CUDA hot path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances (fp64): operator kernels 1e-12 relative to the field's max; material update
+1e-8 on stress and state (north-star tolerance), tangent 1e-6."""
+import numpy as np
+import pytest
+
+import hotpath_cases as hc
+
+pytestmark = pytest.mark.gpu
+
+OP_TOL = 1e-12
+MAT_TOL = 1e-8
+
+
+def _compare(case, gpu, cpu):
+    assert gpu["nfail"] == 0 and cpu["nfail"] == 0
+    assert hc.rel_err(gpu["jac"], cpu["jac"]) < 1e-14
+    assert hc.rel_err(gpu["stress1"], cpu["stress1"]) < MAT_TOL
+    nsv = case["nsv"]
+    hg, hcpu = gpu["hist1"].reshape(-1, nsv), cpu["hist1"].reshape(-1, nsv)
+    cols = [i for i in range(nsv) if i != 3]  # slot 3 = solver evaluation count (bookkeeping)
+    for c in cols:
+        scale = max(np.abs(hcpu[:, c]).max(), 1e-12)
+        assert np.abs(hg[:, c] - hcpu[:, c]).max() / scale < 1e-7, c
+    assert hc.rel_err(gpu["matgrad"], cpu["matgrad"]) < 1e-6
+    assert hc.rel_err(gpu["avg_stress"], cpu["avg_stress"]) < MAT_TOL
+    assert abs(gpu["vol"] - cpu["vol"]) / cpu["vol"] < 1e-13
+
+
+@pytest.mark.parametrize("n,xtal,kin", [(3, 0, 0), (4, 0, 0), (5, 1, 0), (4, 0, 1), (4, 1, 2), (4, 0, 2)])
+def test_material_update_matches_oracle(n, xtal, kin):
+    case = hc.make_case(n=n, seed=10 + n, ngrains=5, xtal=xtal, kin=kin)
+    gpu = hc.run_gpu_hot_path(case)
+    cpu = hc.run_oracle_hot_path(case)
+    _compare(case, gpu, cpu)
+
+
+def test_material_update_evec_entry_point():
+    case = hc.make_case(n=3, seed=3, ngrains=3)
+    gpu = hc.run_gpu_hot_path(case, evec=True)
+    cpu = hc.run_oracle_hot_path(case)
+    _compare(case, gpu, cpu)
+
+
+def _operator_case(case):
+    """Operator kernels are compared on the ORACLE's stress/tangent so that material round-off does not
+    enter: feed the oracle's matgrad/stress to the GPU operator entry points."""
+    import torch
+    from exaconstit_b200 import capi
+    cpu = hc.run_oracle_hot_path(case)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    T = lambda a: torch.tensor(np.ascontiguousarray(a), **f64)
+    ne, nn, dt = case["ne"], case["nn"], case["dt"]
+    ctx = capi.Context(case["xtal"], case["kin"], case["props"], 298.0, ne, nn, case["e2n"], case["assembly"],
+                       case["integ"])
+    ctx.set_essential_mask(case["essmask"])
+    jac, mg, s1 = T(cpu["jac"]), T(cpu["matgrad"]), T(cpu["stress1"])
+    out = {}
+    r = torch.empty(3 * nn, **f64)
+    ctx.residual(jac, s1, r)
+    out["resid"] = r.cpu().numpy()
+    rE = torch.zeros(ne * 24, **f64)
+    ctx.residual_evec(jac, s1, rE)
+    out["resid_E"] = rE.cpu().numpy()
+    ctx.grad_setup(dt, mg, jac)
+    y = torch.empty(3 * nn, **f64)
+    ctx.grad_mult(T(case["xvec"]), y)
+    out["y_grad"] = y.cpu().numpy()
+    from oracle import orc
+    yE = torch.zeros(ne * 24, **f64)
+    ctx.grad_mult_evec(T(orc.gather(case["e2n"], case["xvec"])), yE)
+    out["y_grad_E_full"] = yE.cpu().numpy()
+    d = torch.empty(3 * nn, **f64)
+    ctx.grad_diag(d)
+    out["diag"] = d.cpu().numpy()
+    dE = torch.zeros(ne * 24, **f64)
+    ctx.grad_diag_evec(dE)
+    out["diag_E"] = dE.cpu().numpy()
+    # local action (no essential masking) for GetUpdateBCsAction
+    yl = torch.empty(3 * nn, **f64)
+    ctx.grad_mult(T(case["xvec"]), yl, local_action=True)
+    out["y_local"] = yl.cpu().numpy()
+    if case["assembly"] == 1:
+        ea = torch.zeros(ne * 576, **f64)
+        ctx.ea_assemble(dt, mg, jac, ea)
+        out["ea"] = ea.cpu().numpy()
+    ctx.close()
+    return out, cpu
+
+
+@pytest.mark.parametrize("n,assembly,integ", [(3, 0, 0), (5, 0, 0), (8, 0, 0), (3, 1, 0), (4, 1, 1), (5, 1, 1)])
+def test_operator_kernels_match_oracle(n, assembly, integ):
+    from oracle import orc
+    case = hc.make_case(n=n, seed=20 + n, ngrains=4, assembly=assembly, integ=integ)
+    gpu, cpu = _operator_case(case)
+    for k in ("resid", "resid_E", "y_grad", "y_grad_E_full", "diag", "diag_E"):
+        assert hc.rel_err(gpu[k], cpu[k]) < OP_TOL, k
+    if assembly == 1:
+        assert hc.rel_err(gpu["ea"], cpu["ea"]) < OP_TOL
+    yl = orc.scatter_add(case["e2n"], cpu["y_grad_E_full"], case["nn"])
+    assert hc.rel_err(gpu["y_local"], yl) < OP_TOL
+
+
+def test_grad_mult_properties_at_scale():
+    """Size-independent properties on a mesh too large for the oracle to be the judge in seconds:
+    linearity, symmetry of the operator for symmetric tangents (<x, K y> == <y, K x>), and invariance to
+    the persistent-grid size."""
+    import torch
+    from exaconstit_b200 import capi
+    from oracle import orc
+    n = 24
+    e2n, coords = orc.voxel_mesh(n, n, n)
+    ne, nn = n ** 3, (n + 1) ** 3
+    rng = np.random.default_rng(5)
+    coords = coords + 0.1 / n * (rng.random(coords.size) - 0.5)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    import refcases
+    ctx = capi.Context(0, 0, refcases.goldens()["props_cp_voce"], 298.0, ne, nn, e2n)
+    jac = torch.empty(ne * 72, **f64)
+    ctx.setup_jacobians(torch.tensor(coords, **f64), None, 0.0, jac)
+    S = torch.randn(ne * 8, 6, 6, **f64)
+    K = (S + S.transpose(1, 2) + 12 * torch.eye(6, **f64)).contiguous().reshape(-1)
+    ctx.grad_setup(0.3, K, jac)
+    x1, x2 = torch.randn(3 * nn, **f64), torch.randn(3 * nn, **f64)
+    y1, y2, y12 = (torch.empty(3 * nn, **f64) for _ in range(3))
+    ctx.grad_mult(x1, y1)
+    ctx.grad_mult(x2, y2)
+    ctx.grad_mult(2.0 * x1 - 3.0 * x2, y12)
+    scale = y12.abs().max()
+    assert ((2.0 * y1 - 3.0 * y2 - y12).abs().max() / scale).item() < 1e-12
+    a, b = torch.dot(x1, y2).item(), torch.dot(x2, y1).item()
+    assert abs(a - b) / abs(a) < 1e-10
+    ctx.set_tuning(3)
+    y1b = torch.empty_like(y1)
+    ctx.grad_mult(x1, y1b)
+    assert ((y1 - y1b).abs().max() / y1.abs().max()).item() < 1e-13
+    # constant (rigid translation) vectors are in the null space
+    ones = torch.ones(3 * nn, **f64)
+    y0 = torch.empty_like(ones)
+    ctx.grad_mult(ones, y0)
+    assert (y0.abs().max() / scale).item() < 1e-12
+    ctx.close()
