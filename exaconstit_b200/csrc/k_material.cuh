@@ -263,11 +263,13 @@ __device__ inline bool lu_factor8(double* A, int* piv) {
   return true;
 }
 __device__ inline void lu_solve8(const double* A, const int* piv, double* b) {
+  // rows of L were swapped in full during factorisation: apply every interchange first
   for (int k = 0; k < 8; ++k) {
     const int p = piv[k];
     if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
-    for (int i = k + 1; i < 8; ++i) b[i] -= A[i * 8 + k] * b[k];
   }
+  for (int k = 0; k < 8; ++k)
+    for (int i = k + 1; i < 8; ++i) b[i] -= A[i * 8 + k] * b[k];
   for (int i = 7; i >= 0; --i) {
     double s = b[i];
     for (int j = i + 1; j < 8; ++j) s -= A[i * 8 + j] * b[j];
