@@ -176,5 +176,5 @@ class Context:
     def launch_count(self):
         return lib().exab200_launch_count(self._h)
 
-    def set_tuning(self, ctas_per_sm):
-        _chk(lib().exab200_set_tuning(self._h, ctas_per_sm))
+    def set_tuning(self, ctas_per_sm, variant=0):
+        _chk(lib().exab200_set_tuning(self._h, ctas_per_sm, variant))

@@ -26,9 +26,6 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
   } while (0)
 
-// PA gradient apply configuration: tile of 16 elements (128 threads), 4-stage ring.
-constexpr int kEPT = 16;
-constexpr int kStages = 4;
 }  // namespace
 
 struct exab200_ctx {
@@ -46,6 +43,7 @@ struct exab200_ctx {
   double* d_ea = nullptr;  // EA element matrices (assembly == EA)
   long launches = 0;
   int ctas_per_sm = 1;
+  int variant = 0;  // PA gradient-apply tile configuration, see kVariants
 };
 
 static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((nelems * 8 + threads - 1) / threads); }
@@ -58,18 +56,35 @@ static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((ne
   } while (0)
 
 
-template <int MODE, bool ESS>
-static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
-  using SM = GradMultSmem<kEPT, kStages>;
-  const long ntiles = (c->cfg.nelems + kEPT - 1) / kEPT;
+// PA gradient-apply tile configurations {elements per tile, pipeline stages}; smem/CTA =
+// stages * ept * 2896 B, so variant 0 runs 1 CTA (128 thr) per SM, 1 -> 2 CTAs, 2 -> 1 CTA of 256 thr,
+// 3 -> up to 4 CTAs of 64 thr.
+template <int EPT, int STAGES, int MODE, bool ESS>
+static int launch_gm(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
+  using SM = GradMultSmem<EPT, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_grad_mult_pa<EPT, STAGES, MODE, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+    attr_set = true;
+  }
+  const long ntiles = (c->cfg.nelems + EPT - 1) / EPT;
   long grid = (long)c->sm_count * c->ctas_per_sm;
   if (grid > ntiles) grid = ntiles;
-  k_grad_mult_pa<kEPT, kStages, MODE, ESS><<<(unsigned)grid, kEPT * 8, sizeof(SM), st>>>(c->d_matgrad, c->d_jac, x, y, io,
-                                                                                          c->cfg.nelems, c->grad_dt);
+  k_grad_mult_pa<EPT, STAGES, MODE, ESS><<<(unsigned)grid, EPT * 8, sizeof(SM), st>>>(c->d_matgrad, c->d_jac, x, y, io,
+                                                                                       c->cfg.nelems, c->grad_dt);
   POST_LAUNCH(c);
   return 0;
 }
-
+template <int MODE, bool ESS>
+static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
+  switch (c->variant) {
+    case 1: return launch_gm<16, 2, MODE, ESS>(c, x, y, io, st);
+    case 2: return launch_gm<32, 2, MODE, ESS>(c, x, y, io, st);
+    case 3: return launch_gm<8, 4, MODE, ESS>(c, x, y, io, st);
+    case 4: return launch_gm<16, 3, MODE, ESS>(c, x, y, io, st);
+    default: return launch_gm<16, 4, MODE, ESS>(c, x, y, io, st);
+  }
+}
 
 __global__ void k_set_ess_one(double* __restrict__ v, const unsigned char* __restrict__ ess, long nnodes) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,12 +160,6 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
   CK(cudaMalloc(&c->d_fail, sizeof(int)));
   CK(cudaMemset(c->d_fail, 0, sizeof(int)));
   if (cfg->assembly == EXAB200_EA) CK(cudaMalloc(&c->d_ea, sizeof(double) * 576 * cfg->nelems));
-  {
-    using SM = GradMultSmem<kEPT, kStages>;
-    CK(cudaFuncSetAttribute(k_grad_mult_pa<kEPT, kStages, LVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-    CK(cudaFuncSetAttribute(k_grad_mult_pa<kEPT, kStages, LVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-    CK(cudaFuncSetAttribute(k_grad_mult_pa<kEPT, kStages, EVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
-  }
   *out = c;
   return 0;
 }
@@ -167,9 +176,10 @@ void exab200_destroy(exab200_ctx* c) {
 
 int exab200_num_state_vars(const exab200_ctx* c) { return c ? c->mat.nhist : -1; }
 long exab200_launch_count(const exab200_ctx* c) { return c ? c->launches : -1; }
-int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm) {
-  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8) return fail("bad tuning");
+int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
+  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8 || variant < 0 || variant > 4) return fail("bad tuning");
   c->ctas_per_sm = ctas_per_sm;
+  c->variant = variant;
   return 0;
 }
 

@@ -1,0 +1,783 @@
+// Host side of the hot path: C++ classes that mirror the reference's plugin/operator interface
+// (same names, argument meaning and error behaviour) and drive the exab200 C ABI.  MFEM is absent
+// in this image, so the few MFEM facilities the path needs (device vectors, CG, the L<->E
+// restriction, shared-dof sums) are provided here for the structured voxel mesh; with MFEM present
+// the same classes sit behind mfem::Vector Read()/Write() pointers.
+//
+//   ExaModel / ExaCMechModel            src/mechanics_model.hpp:17-241, src/mechanics_ecmech.hpp:12-107
+//   NonlinearMechOperator               src/mechanics_operator.hpp, src/mechanics_operator.cpp:288-483
+//   gradient operator (PA/EA ext)       src/mechanics_operator_ext.cpp:95-174,228-328
+//   MechOperatorJacobiSmoother          src/mechanics_operator_ext.cpp:11-55
+//   CGSolver                            mfem::CGSolver as configured at src/system_driver.cpp:166-178
+//   ExaNewtonSolver / ExaNewtonLSSolver src/mechanics_solver.cpp:39-143,155-280
+//   SystemDriver                        src/system_driver.cpp:221-319,327-333,429-468
+//
+// Multi-GPU: one process per GPU, z-slab element partition; each rank keeps a local L-vector with
+// both interface node planes.  The only data-path exchanges are (i) the sum of interface-plane
+// partial results with the two z-neighbours after every operator/residual/diagonal action
+// (ncclSend/ncclRecv pair inside one group) and (ii) ncclAllReduce of the CG / Newton scalars.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/exab200.h"
+#include "../../include/exahost.h"
+
+namespace exahost {
+
+static thread_local std::string g_err;
+struct Abort { std::string msg; };  // the reference calls MFEM_ABORT; we unwind to the C boundary
+#define HCK(call)                                                                           \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) throw Abort{std::string(#call) + ": " + cudaGetErrorString(e_)}; \
+  } while (0)
+#define XCK(call)                                                    \
+  do {                                                               \
+    if ((call) != 0) throw Abort{std::string(exab200_last_error())}; \
+  } while (0)
+
+// ---------------------------------------------------------------- NCCL (resolved lazily) ----
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+#define SYM(f, n) f = reinterpret_cast<decltype(f)>(dlsym(h, n))
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return GetUniqueId && CommInitRank && AllReduce && Send && Recv && GroupStart && GroupEnd;
+  }
+};
+static NcclApi g_nccl;
+#define NCK(call)                                                                                   \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess) throw Abort{std::string(#call) + ": " + g_nccl.GetErrorString(r_)};      \
+  } while (0)
+
+// ---------------------------------------------------------------- device vector -------------
+struct Vector {
+  double* d = nullptr;
+  long n = 0;
+  Vector() = default;
+  explicit Vector(long n_) { SetSize(n_); }
+  Vector(const Vector&) = delete;
+  Vector& operator=(const Vector&) = delete;
+  ~Vector() { cudaFree(d); }
+  void SetSize(long n_) {
+    if (n_ == n) return;
+    cudaFree(d);
+    d = nullptr;
+    n = n_;
+    if (n > 0) HCK(cudaMalloc(&d, sizeof(double) * n));
+  }
+  long Size() const { return n; }
+  const double* Read() const { return d; }
+  double* Write() { return d; }
+  double* ReadWrite() { return d; }
+};
+
+// ---------------------------------------------------------------- vector kernels ------------
+constexpr int kRedBlocks = 592;  // 4 x 148 SMs
+__global__ void __launch_bounds__(256) k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, long nn,
+                                                     long n_owned, double* __restrict__ partial) {
+  // dot over the owned nodes of a byNODES L-vector: comps c in 0..2, nodes [0, n_owned)
+  double s = 0.0;
+  const long total = 3 * n_owned;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long c = i / n_owned, n = i - c * n_owned;
+    s += a[c * nn + n] * b[c * nn + n];
+  }
+  __shared__ double red[8];
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_dot_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += partial[i];
+  __shared__ double red[8];
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    *out = t;
+  }
+}
+// x += alpha d ; r -= alpha z     (CG update, fused)
+__global__ void k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
+                            const double* __restrict__ z, double alpha, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { x[i] += alpha * d[i]; r[i] -= alpha * z[i]; }
+}
+// d = z + beta d
+__global__ void k_xpby(double* __restrict__ d, const double* __restrict__ z, double beta, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = z[i] + beta * d[i];
+}
+// y = a x + b y
+__global__ void k_axpby(double* __restrict__ y, const double* __restrict__ x, double a, double b, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + b * y[i];
+}
+// y = dinv .* r
+__global__ void k_jacobi(double* __restrict__ y, const double* __restrict__ dinv, const double* __restrict__ r, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = dinv[i] * r[i];
+}
+__global__ void k_jacobi_setup(double* __restrict__ dinv, const double* __restrict__ diag, const unsigned char* __restrict__ ess,
+                               long nn, double damping) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * nn) return;
+  const long c = i / nn, n = i - c * nn;
+  dinv[i] = ((ess[n] >> c) & 1) ? damping : damping / diag[i];
+}
+// v[ess] = val[ess]    (UpdateVelocity);  with keep_other=false also zero the non-essential dofs
+__global__ void k_set_ess(double* __restrict__ v, const double* __restrict__ val, const unsigned char* __restrict__ ess,
+                          long nn, int mode /*0: v[ess]=val; 1: v = ess ? val - v : 0; 2: v[ess] = 0*/,
+                          const double* __restrict__ other) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * nn) return;
+  const long c = i / nn, n = i - c * nn;
+  const bool e = (ess[n] >> c) & 1;
+  if (mode == 0) { if (e) v[i] = val[i]; }
+  else if (mode == 1) v[i] = e ? (val[i] - other[i]) : 0.0;
+  else if (mode == 2) { if (e) v[i] = 0.0; }
+  else if (mode == 3) { if (e) v[i] = 1.0; }
+}
+// interface-plane add: dst[c*nn + off + i] += src[c*plane + i]
+__global__ void k_plane_add(double* __restrict__ v, const double* __restrict__ buf, long nn, long off, long plane) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * plane) return;
+  const long c = i / plane, n = i - c * plane;
+  v[c * nn + off + n] += buf[i];
+}
+__global__ void k_plane_pack(const double* __restrict__ v, double* __restrict__ buf, long nn, long off, long plane) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * plane) return;
+  const long c = i / plane, n = i - c * plane;
+  buf[i] = v[c * nn + off + n];
+}
+static long g_host_launches = 0;
+static inline unsigned nb(long n) { ++g_host_launches; return (unsigned)((n + 255) / 256); }
+
+// ---------------------------------------------------------------- communicator --------------
+class SlabComm {
+ public:
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  cudaStream_t stream = nullptr;
+  long nn = 0, plane = 0, n_owned = 0;
+  Vector send_lo, send_hi, recv_lo, recv_hi, partial, scal;
+  double* h_scal = nullptr;  // pinned
+  long n_allreduce = 0, n_halo = 0;
+
+  void Init(int rank_, int nranks_, const void* nccl_id, cudaStream_t s, long nn_, long plane_) {
+    rank = rank_; nranks = nranks_; stream = s; nn = nn_; plane = plane_;
+    n_owned = (rank == nranks - 1) ? nn : nn - plane;
+    partial.SetSize(kRedBlocks);
+    scal.SetSize(8);
+    HCK(cudaMallocHost(&h_scal, 8 * sizeof(double)));
+    if (nranks > 1) {
+      if (!g_nccl.load()) throw Abort{"NCCL library could not be loaded"};
+      ncclUniqueId id;
+      std::memcpy(&id, nccl_id, sizeof(id));
+      NCK(g_nccl.CommInitRank(&comm, nranks, id, rank));
+      send_lo.SetSize(3 * plane); send_hi.SetSize(3 * plane); recv_lo.SetSize(3 * plane); recv_hi.SetSize(3 * plane);
+    }
+  }
+  ~SlabComm() {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    if (h_scal) cudaFreeHost(h_scal);
+  }
+  // Sum the partial results living on the interface planes with the z-neighbours (the role of
+  // P->MultTranspose followed by P->Mult in the reference, src/mechanics_operator_ext.cpp:149,157).
+  void HaloSum(double* v) {
+    if (nranks == 1) return;
+    const bool lo = rank > 0, hi = rank < nranks - 1;
+    const long top = nn - plane;
+    if (lo) k_plane_pack<<<nb(3 * plane), 256, 0, stream>>>(v, send_lo.d, nn, 0, plane);
+    if (hi) k_plane_pack<<<nb(3 * plane), 256, 0, stream>>>(v, send_hi.d, nn, top, plane);
+    NCK(g_nccl.GroupStart());
+    if (lo) { NCK(g_nccl.Send(send_lo.d, 3 * plane, ncclDouble, rank - 1, comm, stream)); NCK(g_nccl.Recv(recv_lo.d, 3 * plane, ncclDouble, rank - 1, comm, stream)); }
+    if (hi) { NCK(g_nccl.Send(send_hi.d, 3 * plane, ncclDouble, rank + 1, comm, stream)); NCK(g_nccl.Recv(recv_hi.d, 3 * plane, ncclDouble, rank + 1, comm, stream)); }
+    NCK(g_nccl.GroupEnd());
+    if (lo) k_plane_add<<<nb(3 * plane), 256, 0, stream>>>(v, recv_lo.d, nn, 0, plane);
+    if (hi) k_plane_add<<<nb(3 * plane), 256, 0, stream>>>(v, recv_hi.d, nn, top, plane);
+    ++n_halo;
+  }
+  // global dot product over uniquely-owned dofs; blocking (returns the value on the host)
+  double Dot(const double* a, const double* b) {
+    k_dot_partial<<<kRedBlocks, 256, 0, stream>>>(a, b, nn, n_owned, partial.d);
+    k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, scal.d);
+    g_host_launches += 2;
+    if (nranks > 1) { NCK(g_nccl.AllReduce(scal.d, scal.d, 1, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    HCK(cudaMemcpyAsync(h_scal, scal.d, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    HCK(cudaStreamSynchronize(stream));
+    return h_scal[0];
+  }
+  // sum-reduce a small device buffer in place and fetch it
+  void AllReduceFetch(double* d_buf, int n, double* h_out) {
+    if (nranks > 1) { NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    HCK(cudaMemcpyAsync(h_scal, d_buf, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    HCK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n; ++i) h_out[i] = h_scal[i];
+  }
+};
+
+// ---------------------------------------------------------------- ExaModel ------------------
+enum class Assembly { PA = EXAB200_PA, EA = EXAB200_EA };
+
+// Plugin surface of src/mechanics_model.hpp:17-241 (quadrature data as raw device arrays).
+class ExaModel {
+ public:
+  int numProps, numStateVars;
+  double dt = 0.0, t = 0.0;
+  Vector *stress0, *stress1, *matGrad, *matVars0, *matVars1;
+  Assembly assembly;
+  ExaModel(Vector* s0, Vector* s1, Vector* mg, Vector* v0, Vector* v1, int nProps, int nStateVars, Assembly a)
+      : numProps(nProps), numStateVars(nStateVars), stress0(s0), stress1(s1), matGrad(mg), matVars0(v0), matVars1(v1), assembly(a) {}
+  virtual ~ExaModel() {}
+  // src/mechanics_model.hpp:109-111; `vel` is the velocity L-vector here (restriction fused in the kernel)
+  virtual void ModelSetup(const int nqpts, const int nelems, const int space_dim, const int nnodes, const Vector& jacobian,
+                          const Vector& loc_grad, const Vector& vel) = 0;
+  virtual void UpdateModelVars() = 0;
+  void SetModelDt(double dt_) { dt = dt_; }
+  double GetModelDt() const { return dt; }
+  void UpdateStress() { std::swap(stress0->d, stress1->d); }        // src/mechanics_model.cpp:435-438
+  void UpdateStateVars() { std::swap(matVars0->d, matVars1->d); }   // src/mechanics_model.cpp:440-443
+};
+
+class ExaCMechModel : public ExaModel {
+ public:
+  exab200_ctx* ctx;
+  cudaStream_t stream;
+  long model_setups = 0;
+  ExaCMechModel(exab200_ctx* c, cudaStream_t s, Vector* s0, Vector* s1, Vector* mg, Vector* v0, Vector* v1, int nProps,
+                Assembly a)
+      : ExaModel(s0, s1, mg, v0, v1, nProps, exab200_num_state_vars(c), a), ctx(c), stream(s) {}
+  void ModelSetup(const int, const int, const int, const int, const Vector& jacobian, const Vector&, const Vector& vel) override {
+    XCK(exab200_model_setup(ctx, dt, jacobian.Read(), vel.Read(), stress0->Read(), matVars0->Read(), stress1->Write(),
+                            matVars1->Write(), matGrad->Write(), stream));
+    ++model_setups;
+  }
+  void UpdateModelVars() override {}
+};
+
+// ---------------------------------------------------------------- operators -----------------
+class Operator {
+ public:
+  virtual ~Operator() {}
+  virtual void Mult(const Vector& x, Vector& y) const = 0;
+};
+
+class NonlinearMechOperator;
+
+// The matrix-free gradient (PA or EA flavour, src/mechanics_operator_ext.cpp:63-328).
+class GradientOperator : public Operator {
+ public:
+  const NonlinearMechOperator* op;
+  bool local_action = false;
+  explicit GradientOperator(const NonlinearMechOperator* o) : op(o) {}
+  void Mult(const Vector& x, Vector& y) const override;       // TMult<false>
+  void LocalMult(const Vector& x, Vector& y) const;           // TMult<true>
+  void AssembleDiagonal(Vector& diag) const;
+};
+
+class NonlinearMechOperator : public Operator {
+ public:
+  exab200_ctx* ctx;
+  SlabComm* comm;
+  cudaStream_t stream;
+  ExaModel* model;
+  long nelems, nnodes;
+  Vector* x_beg;                 // beginning-of-step coordinates (L-vector)
+  mutable Vector el_jac, diag;
+  mutable GradientOperator jacobian;
+  Vector ess_mask_dev;           // device copy of the per-node essential mask (bytes)
+  mutable long grad_mults = 0, residuals = 0;
+  mutable double t_setup = 0, t_model = 0;
+
+  NonlinearMechOperator(exab200_ctx* c, SlabComm* cm, cudaStream_t s, ExaModel* m, long ne, long nn, Vector* xb)
+      : ctx(c), comm(cm), stream(s), model(m), nelems(ne), nnodes(nn), x_beg(xb), el_jac(ne * 72), diag(3 * nn), jacobian(this) {}
+
+  // src/mechanics_operator.cpp:279-285
+  void UpdateEssTDofs(const unsigned char* h_mask) { XCK(exab200_set_essential_mask(ctx, h_mask)); }
+
+  // src/mechanics_operator.cpp:311-348: end coordinates, Jacobians, material update
+  template <bool upd_crds>
+  void Setup(const Vector& k) const {
+    XCK(exab200_setup_jacobians(ctx, x_beg->Read(), upd_crds ? k.Read() : nullptr, model->dt, el_jac.Write(), stream));
+    model->ModelSetup(8, (int)nelems, 3, 8, el_jac, el_jac /*shape gradients are analytic in-kernel*/, k);
+  }
+  // src/mechanics_operator.cpp:288-308: y = H(k)
+  void Mult(const Vector& k, Vector& y) const override {
+    Setup<true>(k);
+    XCK(exab200_residual(ctx, el_jac.Read(), model->stress1->Read(), y.Write(), stream));
+    comm->HaloSum(y.Write());
+    ++residuals;
+  }
+  // src/mechanics_operator.cpp:436-443
+  Operator& GetGradient(const Vector&) const {
+    XCK(exab200_grad_setup(ctx, model->dt, model->matGrad->Read(), el_jac.Read(), stream));
+    jacobian.AssembleDiagonal(diag);
+    return jacobian;
+  }
+  // src/mechanics_operator.cpp:446-483
+  Operator& GetUpdateBCsAction(const Vector& k, const Vector& x, Vector& y) const {
+    Setup<false>(k);
+    Vector resid(y.Size());
+    XCK(exab200_grad_setup(ctx, model->dt, model->matGrad->Read(), el_jac.Read(), stream));
+    jacobian.LocalMult(x, y);
+    XCK(exab200_residual(ctx, el_jac.Read(), model->stress1->Read(), resid.Write(), stream));
+    comm->HaloSum(resid.Write());
+    ++residuals;
+    // y[ess] = 0; y += resid
+    k_set_ess<<<nb(3 * nnodes), 256, 0, stream>>>(y.Write(), nullptr, ess_dev(), nnodes, 2, nullptr);
+    k_axpby<<<nb(3 * nnodes), 256, 0, stream>>>(y.Write(), resid.Read(), 1.0, 1.0, 3 * nnodes);
+    HCK(cudaStreamSynchronize(stream));  // resid goes out of scope
+    return jacobian;
+  }
+  const unsigned char* ess_dev() const { return reinterpret_cast<const unsigned char*>(ess_mask_dev.d); }
+};
+
+void GradientOperator::Mult(const Vector& x, Vector& y) const {
+  XCK(exab200_grad_mult(op->ctx, x.Read(), y.Write(), 0, op->stream));
+  op->comm->HaloSum(y.Write());
+  ++op->grad_mults;
+}
+void GradientOperator::LocalMult(const Vector& x, Vector& y) const {
+  XCK(exab200_grad_mult(op->ctx, x.Read(), y.Write(), 1, op->stream));
+  op->comm->HaloSum(y.Write());
+  ++op->grad_mults;
+}
+void GradientOperator::AssembleDiagonal(Vector& diag) const {
+  XCK(exab200_grad_diag(op->ctx, diag.Write(), op->stream));
+  // shared nodes: sum partial diagonals, then essential entries back to 1 (they were summed twice)
+  if (op->comm->nranks > 1) {
+    op->comm->HaloSum(diag.Write());
+    k_set_ess<<<nb(3 * op->nnodes), 256, 0, op->stream>>>(diag.Write(), nullptr, op->ess_dev(), op->nnodes, 3, nullptr);
+  }
+}
+
+// src/mechanics_operator_ext.cpp:11-55.  Reference quirk: Setup() runs only in
+// the constructor with diag == 1, so dinv stays 1; `refresh` = true gives a real Jacobi preconditioner.
+class MechOperatorJacobiSmoother {
+ public:
+  long N;
+  Vector dinv;
+  double damping;
+  cudaStream_t stream;
+  bool refresh;
+  MechOperatorJacobiSmoother(long nn, cudaStream_t s, bool refresh_, double dmp = 1.0)
+      : N(3 * nn), dinv(3 * nn), damping(dmp), stream(s), refresh(refresh_) {
+    // dinv = damping / 1
+    std::vector<double> ones(N, damping);
+    HCK(cudaMemcpy(dinv.d, ones.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+  }
+  void Setup(const Vector& diag, const unsigned char* ess, long nn) {
+    k_jacobi_setup<<<nb(N), 256, 0, stream>>>(dinv.Write(), diag.Read(), ess, nn, damping);
+  }
+  void Mult(const Vector& x, Vector& y) const { k_jacobi<<<nb(N), 256, 0, stream>>>(y.Write(), dinv.Read(), x.Read(), N); }
+};
+
+// mfem::CGSolver::Mult, iterative_mode = false, with the smoother as preconditioner.
+class CGSolver {
+ public:
+  SlabComm* comm;
+  cudaStream_t stream;
+  double rel_tol = 1e-7, abs_tol = 1e-27;
+  int max_iter = 1000;
+  const Operator* oper = nullptr;
+  const MechOperatorJacobiSmoother* prec = nullptr;
+  mutable Vector r, d, z;
+  mutable int final_iter = 0, converged = 0;
+  mutable long total_iters = 0;
+  CGSolver(SlabComm* c, cudaStream_t s, long n) : comm(c), stream(s), r(n), d(n), z(n) {}
+  void SetOperator(const Operator& op) { oper = &op; }
+  void Mult(const Vector& b, Vector& x) const {
+    const long n = b.Size();
+    HCK(cudaMemcpyAsync(r.d, b.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    HCK(cudaMemsetAsync(x.d, 0, sizeof(double) * n, stream));
+    prec->Mult(r, z);
+    HCK(cudaMemcpyAsync(d.d, z.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    double nom = comm->Dot(d.d, r.d);
+    const double r0 = std::max(nom * rel_tol * rel_tol, abs_tol * abs_tol);
+    converged = 0;
+    final_iter = 0;
+    if (nom <= r0) { converged = 1; return; }
+    oper->Mult(d, z);
+    double den = comm->Dot(z.d, d.d);
+    if (den <= 0.0 && den == 0.0) return;
+    int i = 1;
+    final_iter = max_iter;
+    for (;;) {
+      const double alpha = nom / den;
+      k_cg_update<<<nb(n), 256, 0, stream>>>(x.d, r.d, d.d, z.d, alpha, n);
+      prec->Mult(r, z);
+      const double betanom = comm->Dot(r.d, z.d);
+      if (betanom <= r0) { converged = 1; final_iter = i; break; }
+      if (++i > max_iter) break;
+      const double beta = betanom / nom;
+      k_xpby<<<nb(n), 256, 0, stream>>>(d.d, z.d, beta, n);
+      oper->Mult(d, z);
+      den = comm->Dot(d.d, z.d);
+      if (den <= 0.0 && den == 0.0) { final_iter = i; break; }
+      nom = betanom;
+    }
+    total_iters += std::min(i, max_iter);
+  }
+};
+
+// src/mechanics_solver.cpp:39-143 (NR) and :155-280 (NRLS)
+class ExaNewtonSolver {
+ public:
+  SlabComm* comm;
+  cudaStream_t stream;
+  const NonlinearMechOperator* oper_mech = nullptr;
+  CGSolver* prec = nullptr;
+  MechOperatorJacobiSmoother* smoother = nullptr;
+  double rel_tol = 5e-5, abs_tol = 5e-10;
+  int max_iter = 25, print_level = -1;
+  bool line_search = false;
+  mutable Vector r, c, x_prev;
+  mutable int final_iter = 0, converged = 0;
+  mutable double final_norm = 0.0;
+  ExaNewtonSolver(SlabComm* cm, cudaStream_t s, long n) : comm(cm), stream(s), r(n), c(n), x_prev(n) {}
+  double Norm(const Vector& v) const { return std::sqrt(comm->Dot(v.d, v.d)); }
+  void CGSolverSolve(Operator& op, const Vector& b, Vector& x) const { prec->SetOperator(op); prec->Mult(b, x); }
+  void Mult(Vector& x) const {
+    const long n = x.Size();
+    oper_mech->Mult(x, r);
+    double norm = Norm(r);
+    const double norm0 = norm;
+    const double norm_max = std::max(rel_tol * norm, abs_tol);
+    double scale = 1.0;
+    int it;
+    for (it = 0; true; ++it) {
+      if (!std::isfinite(norm)) throw Abort{"Newton: residual norm is not finite"};
+      if (print_level >= 0 && comm->rank == 0) {
+        std::printf("Newton iteration %2d : ||r|| = %g", it, norm);
+        if (it > 0) std::printf(", ||r||/||r_0|| = %g", norm / norm0);
+        std::printf("\n");
+      }
+      if (norm <= norm_max) { converged = 1; break; }
+      if (it >= max_iter) { converged = 0; break; }
+      Operator& grad = oper_mech->GetGradient(x);
+      if (smoother->refresh) smoother->Setup(oper_mech->diag, oper_mech->ess_dev(), oper_mech->nnodes);
+      prec->SetOperator(grad);
+      prec->Mult(r, c);
+      if (line_search) {
+        HCK(cudaMemcpyAsync(x_prev.d, x.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+        k_axpby<<<nb(n), 256, 0, stream>>>(x.d, c.d, -1.0, 1.0, n);
+        oper_mech->Mult(x, r);
+        const double q1 = norm, q3 = Norm(r);
+        HCK(cudaMemcpyAsync(x.d, x_prev.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+        k_axpby<<<nb(n), 256, 0, stream>>>(x.d, c.d, -0.5, 1.0, n);
+        oper_mech->Mult(x, r);
+        const double q2 = Norm(r);
+        const double eps = (3.0 * q1 - 4.0 * q2 + q3) / (4.0 * (q1 - 2.0 * q2 + q3));
+        if ((q1 - 2.0 * q2 + q3) > 0 && eps > 0 && eps < 1) scale = eps;
+        else if (q3 < q1) scale = 1.0;
+        else scale = 0.05;
+        HCK(cudaMemcpyAsync(x.d, x_prev.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+      }
+      k_axpby<<<nb(n), 256, 0, stream>>>(x.d, c.d, -scale, 1.0, n);
+      oper_mech->Mult(x, r);
+      const double norm_prev = norm;
+      norm = Norm(r);
+      if (!line_search) scale = (norm / norm_prev > 0.5) ? 0.5 : 1.0;
+    }
+    final_iter = it;
+    final_norm = norm;
+  }
+};
+
+}  // namespace exahost
+
+using namespace exahost;
+
+// ---------------------------------------------------------------- SystemDriver + C API ------
+struct exahost_sim {
+  exahost_config cfg;
+  cudaStream_t stream = nullptr;
+  exab200_ctx* ctx = nullptr;
+  SlabComm comm;
+  long nelems = 0, nnodes = 0, plane = 0;
+  Vector stress0, stress1, matVars0, matVars1, matGrad;
+  Vector x_beg, v_sol, v_prev, ess_val, tmp, sums;
+  std::vector<unsigned char> h_mask;
+  std::unique_ptr<ExaCMechModel> model;
+  std::unique_ptr<NonlinearMechOperator> oper;
+  std::unique_ptr<MechOperatorJacobiSmoother> smoother;
+  std::unique_ptr<CGSolver> cg;
+  std::unique_ptr<ExaNewtonSolver> newton;
+  double* h_pinned = nullptr;  // staging for host-buffer steps
+  long newton_total = 0;
+
+  // SystemDriver::UpdateVelocity (src/system_driver.cpp:327-333)
+  void UpdateVelocity() {
+    k_set_ess<<<nb(3 * nnodes), 256, 0, stream>>>(v_sol.d, ess_val.d, oper->ess_dev(), nnodes, 0, nullptr);
+  }
+  // SystemDriver::SolveInit (src/system_driver.cpp:293-319)
+  void SolveInit() {
+    const long n = 3 * nnodes;
+    Vector deltaF(n), b(n), x(n);
+    // deltaF = ess ? v_sol - v_prev : 0
+    k_set_ess<<<nb(n), 256, 0, stream>>>(deltaF.d, v_sol.d, oper->ess_dev(), nnodes, 1, v_prev.d);
+    Operator& op = oper->GetUpdateBCsAction(v_prev, deltaF, b);
+    newton->CGSolverSolve(op, b, x);
+    // v_sol = -x + v_prev
+    HCK(cudaMemcpyAsync(v_sol.d, v_prev.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    k_axpby<<<nb(n), 256, 0, stream>>>(v_sol.d, x.d, -1.0, 1.0, n);
+    HCK(cudaStreamSynchronize(stream));
+  }
+  // SystemDriver::UpdateModel (src/system_driver.cpp:429-468): swap + volume-averaged stress
+  void UpdateModel(double* avg_stress) {
+    model->UpdateModelVars();
+    model->UpdateStress();
+    model->UpdateStateVars();
+    XCK(exab200_vol_sum(ctx, oper->el_jac.Read(), stress0.Read(), 6, sums.Write(), stream));
+    double h[7];
+    comm.AllReduceFetch(sums.d, 7, h);
+    for (int i = 0; i < 6; ++i) avg_stress[i] = h[i] / h[6];
+  }
+};
+
+extern "C" {
+
+const char* exahost_last_error(void) { return g_err.c_str(); }
+
+int exahost_nccl_unique_id(void* out128) {
+  if (!g_nccl.load()) { g_err = "NCCL library could not be loaded"; return 1; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_err = "ncclGetUniqueId failed"; return 1; }
+  std::memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+
+int exahost_create(const exahost_config* cfg, exahost_sim** out) {
+  exahost_sim* s = nullptr;
+  try {
+    s = new exahost_sim();
+    s->cfg = *cfg;
+    HCK(cudaSetDevice(cfg->device));
+    HCK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const long nx = cfg->nx, ny = cfg->ny, nzl = cfg->nz_local;
+    s->nelems = nx * ny * nzl;
+    s->plane = (nx + 1) * (ny + 1);
+    s->nnodes = s->plane * (nzl + 1);
+    // element -> node map, NATIVE hex vertex order (Mesh::MakeCartesian3D, x fastest)
+    std::vector<int> e2n(8 * s->nelems);
+    static const int hv[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    for (long k = 0; k < nzl; ++k)
+      for (long j = 0; j < ny; ++j)
+        for (long i = 0; i < nx; ++i) {
+          const long e = (k * ny + j) * nx + i;
+          for (int a = 0; a < 8; ++a)
+            e2n[e * 8 + a] = (int)(((k + hv[a][2]) * (ny + 1) + (j + hv[a][1])) * (nx + 1) + (i + hv[a][0]));
+        }
+    exab200_config ec;
+    ec.xtal = cfg->xtal; ec.slip = cfg->slip; ec.nprops = cfg->nprops; ec.props = cfg->props; ec.temp_k = cfg->temp_k;
+    ec.nelems = s->nelems; ec.nnodes = s->nnodes; ec.e2n = e2n.data(); ec.assembly = cfg->assembly; ec.integ = cfg->integ;
+    ec.device = cfg->device;
+    XCK(exab200_create(&ec, &s->ctx));
+    const int nsv = exab200_num_state_vars(s->ctx);
+    const long npts = s->nelems * 8, n = 3 * s->nnodes;
+    s->stress0.SetSize(npts * 6); s->stress1.SetSize(npts * 6);
+    s->matVars0.SetSize(npts * nsv); s->matVars1.SetSize(npts * nsv);
+    s->matGrad.SetSize(npts * 36);
+    s->x_beg.SetSize(n); s->v_sol.SetSize(n); s->v_prev.SetSize(n); s->ess_val.SetSize(n); s->tmp.SetSize(n);
+    s->sums.SetSize(48);
+    HCK(cudaMemset(s->stress0.d, 0, sizeof(double) * npts * 6));
+    HCK(cudaMemset(s->stress1.d, 0, sizeof(double) * npts * 6));
+    HCK(cudaMemset(s->v_sol.d, 0, sizeof(double) * n));
+    HCK(cudaMemset(s->v_prev.d, 0, sizeof(double) * n));
+    HCK(cudaMemset(s->ess_val.d, 0, sizeof(double) * n));
+    // coordinates (byNODES) of this slab
+    {
+      std::vector<double> xc(n);
+      for (long k = 0; k <= nzl; ++k)
+        for (long j = 0; j <= ny; ++j)
+          for (long i = 0; i <= nx; ++i) {
+            const long nd = (k * (ny + 1) + j) * (nx + 1) + i;
+            xc[nd] = cfg->length[0] * i / nx;
+            xc[s->nnodes + nd] = cfg->length[1] * j / ny;
+            xc[2 * s->nnodes + nd] = cfg->length[2] * (k + cfg->z0) / cfg->nz_total;
+          }
+      HCK(cudaMemcpy(s->x_beg.d, xc.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    // history: setStateVarData (src/mechanics_driver.cpp:1058-1154: state-file values + per-grain quaternion
+    // at offset 9) followed by init_state_vars
+    {
+      std::vector<double> h((size_t)npts * nsv, 0.0);
+      for (long e = 0; e < s->nelems; ++e) {
+        const int g = cfg->grain_ids[e] - 1;
+        if (g < 0 || g >= cfg->ngrains) throw Abort{"grain id out of range"};
+        for (int q = 0; q < 8; ++q)
+          for (int i = 0; i < 4; ++i) h[(size_t)(e * 8 + q) * nsv + 9 + i] = cfg->quats[4 * g + i];
+      }
+      HCK(cudaMemcpy(s->matVars0.d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+      XCK(exab200_hist_init(s->ctx, s->matVars0.d, s->stream));
+      HCK(cudaStreamSynchronize(s->stream));
+    }
+    s->comm.Init(cfg->rank, cfg->nranks, cfg->nccl_id, s->stream, s->nnodes, s->plane);
+    const Assembly as = cfg->assembly == EXAB200_EA ? Assembly::EA : Assembly::PA;
+    s->model.reset(new ExaCMechModel(s->ctx, s->stream, &s->stress0, &s->stress1, &s->matGrad, &s->matVars0, &s->matVars1,
+                                     cfg->nprops, as));
+    s->oper.reset(new NonlinearMechOperator(s->ctx, &s->comm, s->stream, s->model.get(), s->nelems, s->nnodes, &s->x_beg));
+    s->oper->ess_mask_dev.SetSize((s->nnodes + 7) / 8 + 1);
+    s->h_mask.assign(s->nnodes, 0);
+    HCK(cudaMemset(s->oper->ess_mask_dev.d, 0, s->nnodes));
+    s->smoother.reset(new MechOperatorJacobiSmoother(s->nnodes, s->stream, cfg->true_jacobi != 0));
+    s->cg.reset(new CGSolver(&s->comm, s->stream, n));
+    s->cg->rel_tol = cfg->krylov_rel_tol; s->cg->abs_tol = cfg->krylov_abs_tol; s->cg->max_iter = cfg->krylov_iter;
+    s->cg->prec = s->smoother.get();
+    s->newton.reset(new ExaNewtonSolver(&s->comm, s->stream, n));
+    s->newton->rel_tol = cfg->newton_rel_tol; s->newton->abs_tol = cfg->newton_abs_tol; s->newton->max_iter = cfg->newton_iter;
+    s->newton->line_search = cfg->nl_solver == 1;
+    s->newton->oper_mech = s->oper.get();
+    s->newton->prec = s->cg.get();
+    s->newton->smoother = s->smoother.get();
+    s->newton->print_level = cfg->verbose ? 0 : -1;
+    HCK(cudaMallocHost(&s->h_pinned, sizeof(double) * n));
+    *out = s;
+    return 0;
+  } catch (const Abort& a) {
+    g_err = a.msg;
+    delete s;
+    return 1;
+  }
+}
+
+void exahost_destroy(exahost_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->cfg.device);
+  cudaStreamSynchronize(s->stream);
+  s->newton.reset(); s->cg.reset(); s->smoother.reset(); s->oper.reset(); s->model.reset();
+  if (s->ctx) exab200_destroy(s->ctx);
+  if (s->h_pinned) cudaFreeHost(s->h_pinned);
+  cudaStream_t st = s->stream;
+  delete s;
+  cudaStreamDestroy(st);
+}
+
+// SystemDriver::UpdateEssBdr (src/system_driver.cpp:321-324): per-node component mask + prescribed values
+int exahost_set_bcs(exahost_sim* s, const unsigned char* mask, const double* h_ess_val) {
+  try {
+    s->h_mask.assign(mask, mask + s->nnodes);
+    s->oper->UpdateEssTDofs(mask);
+    HCK(cudaMemcpy(s->oper->ess_mask_dev.d, mask, s->nnodes, cudaMemcpyHostToDevice));
+    HCK(cudaMemcpy(s->ess_val.d, h_ess_val, sizeof(double) * 3 * s->nnodes, cudaMemcpyHostToDevice));
+    return 0;
+  } catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+
+// One time step of the reference's loop (src/mechanics_driver.cpp:837-907).
+//   bc_changed: run the SolveInit corrector first (src/mechanics_driver.cpp:866-878)
+//   h_ess_val_in  (may be NULL): prescribed velocities for this step, HOST buffer, copied H2D inside the call
+//   h_vel_out     (may be NULL): converged velocity, HOST buffer, copied D2H inside the call
+//   out: {newton_iters, pcg_iters, converged, model_setups, grad_mults, seconds, avg_stress[6]}
+int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out, double* out) {
+  try {
+    HCK(cudaSetDevice(s->cfg.device));
+    const long n = 3 * s->nnodes;
+    auto t0 = std::chrono::steady_clock::now();
+    const long pcg0 = s->cg->total_iters, ms0 = s->model->model_setups, gm0 = s->oper->grad_mults;
+    if (h_ess_val_in) {
+      std::memcpy(s->h_pinned, h_ess_val_in, sizeof(double) * n);
+      HCK(cudaMemcpyAsync(s->ess_val.d, s->h_pinned, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
+    }
+    s->model->SetModelDt(dt);
+    if (bc_changed) {
+      HCK(cudaMemcpyAsync(s->v_prev.d, s->v_sol.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
+      s->UpdateVelocity();
+      s->SolveInit();
+    }
+    s->UpdateVelocity();
+    s->newton->Mult(s->v_sol);
+    if (!s->newton->converged) throw Abort{"Newton Solver did not converge."};  // MFEM_VERIFY, src/system_driver.cpp:287
+    int nfail = 0;
+    XCK(exab200_failed_points(s->ctx, s->stream, &nfail));
+    if (nfail) throw Abort{"material update failed at " + std::to_string(nfail) + " quadrature points"};
+    double avg[6];
+    s->UpdateModel(avg);
+    // x_beg = x_cur (src/mechanics_driver.cpp:907): x_beg += dt * v
+    k_axpby<<<nb(n), 256, 0, s->stream>>>(s->x_beg.d, s->v_sol.d, dt, 1.0, n);
+    if (h_vel_out) {
+      HCK(cudaMemcpyAsync(s->h_pinned, s->v_sol.d, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+      HCK(cudaStreamSynchronize(s->stream));
+      std::memcpy(h_vel_out, s->h_pinned, sizeof(double) * n);
+    }
+    HCK(cudaStreamSynchronize(s->stream));
+    auto t1 = std::chrono::steady_clock::now();
+    s->newton_total += s->newton->final_iter;
+    out[0] = s->newton->final_iter;
+    out[1] = (double)(s->cg->total_iters - pcg0);
+    out[2] = s->newton->converged;
+    out[3] = (double)(s->model->model_setups - ms0);
+    out[4] = (double)(s->oper->grad_mults - gm0);
+    out[5] = std::chrono::duration<double>(t1 - t0).count();
+    for (int i = 0; i < 6; ++i) out[6 + i] = avg[i];
+    return 0;
+  } catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+
+// copy quadrature state to HOST buffers (parity checks): which = 0 stress0 (6/pt), 1 matVars0 (nsv/pt), 2 v_sol, 3 x_beg
+int exahost_get(exahost_sim* s, int which, double* h_out) {
+  try {
+    HCK(cudaSetDevice(s->cfg.device));
+    HCK(cudaStreamSynchronize(s->stream));
+    const Vector* v = which == 0 ? &s->stress0 : which == 1 ? &s->matVars0 : which == 2 ? &s->v_sol : &s->x_beg;
+    HCK(cudaMemcpy(h_out, v->d, sizeof(double) * v->n, cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+
+long exahost_counter(exahost_sim* s, int which) {
+  switch (which) {
+    case 0: return exab200_launch_count(s->ctx) + g_host_launches;
+    case 1: return s->comm.n_allreduce;
+    case 2: return s->comm.n_halo;
+    case 3: return s->model->model_setups;
+    case 4: return s->oper->grad_mults;
+    case 5: return s->cg->total_iters;
+    case 6: return s->newton_total;
+    case 7: return exab200_num_state_vars(s->ctx);
+  }
+  return -1;
+}
+
+void* exahost_stream(exahost_sim* s) { return s->stream; }
+void* exahost_ctx(exahost_sim* s) { return s->ctx; }
+
+}  // extern "C"

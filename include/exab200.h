@@ -131,8 +131,9 @@ int exab200_grad_calc(exab200_ctx* ctx, const double* d_jac, const double* d_fie
 /* Kernel launch counter (all launches issued through this context). */
 long exab200_launch_count(const exab200_ctx* ctx);
 
-/* Tuning knob for the PA gradient apply: persistent CTAs per SM (default 1) -- testing only. */
-int exab200_set_tuning(exab200_ctx* ctx, int ctas_per_sm);
+/* Tuning knobs for the PA gradient apply: persistent CTAs per SM (default 1) and tile variant
+ * (0: 16 elems x 4 stages, 1: 16x2, 2: 32x2, 3: 8x4, 4: 16x3) -- benchmarking only. */
+int exab200_set_tuning(exab200_ctx* ctx, int ctas_per_sm, int variant);
 
 #ifdef __cplusplus
 }

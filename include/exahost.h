@@ -1,0 +1,55 @@
+/* exahost -- C entry points of the C++ host layer (exaconstit_b200/csrc/host_sim.cu) that mirrors the
+ * reference's SystemDriver / NonlinearMechOperator / ExaNewtonSolver / CGSolver classes on top of the
+ * exab200 kernels, for a z-slab of an auto-generated voxel mesh.  These are what bench.py and the
+ * system-level parity tests drive; a reference-side build would instead bind exab200.h directly from
+ * its own classes.
+ */
+#ifndef EXAHOST_H
+#define EXAHOST_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct exahost_sim exahost_sim;
+
+typedef struct {
+  /* mesh: Mesh.Auto (src/mechanics_driver.cpp:247-253): global nx*ny*nz_total hexes, this rank owns
+   * element layers [z0, z0 + nz_local) */
+  int nx, ny, nz_local, z0, nz_total;
+  double length[3];
+  /* Model.ExaCMech + Properties */
+  int xtal, slip, nprops;
+  const double* props;
+  double temp_k;
+  const int* grain_ids; /* nx*ny*nz_local, 1-based, x fastest (grains.txt order) */
+  const double* quats;  /* 4 per grain */
+  int ngrains;
+  /* Solvers */
+  int assembly, integ, nl_solver; /* PA|EA, FULL|BBAR, NR|NRLS */
+  double newton_rel_tol, newton_abs_tol;
+  int newton_iter;
+  double krylov_rel_tol, krylov_abs_tol;
+  int krylov_iter;
+  int true_jacobi; /* 0 = reference behaviour (smoother never refreshed => identity), 1 = Jacobi */
+  /* parallel layout */
+  int rank, nranks, device;
+  const void* nccl_id; /* 128-byte ncclUniqueId shared by all ranks (NULL when nranks == 1) */
+  int verbose;
+} exahost_config;
+
+const char* exahost_last_error(void);
+int exahost_nccl_unique_id(void* out128);
+int exahost_create(const exahost_config* cfg, exahost_sim** out);
+void exahost_destroy(exahost_sim* sim);
+int exahost_set_bcs(exahost_sim* sim, const unsigned char* mask_per_node, const double* h_ess_val_L);
+int exahost_step(exahost_sim* sim, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out,
+                 double* out12);
+int exahost_get(exahost_sim* sim, int which, double* h_out);
+long exahost_counter(exahost_sim* sim, int which);
+void* exahost_stream(exahost_sim* sim);
+void* exahost_ctx(exahost_sim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
