@@ -42,8 +42,8 @@ struct exab200_ctx {
   const double* d_jac = nullptr;
   double* d_ea = nullptr;  // EA element matrices (assembly == EA)
   long launches = 0;
-  int ctas_per_sm = 1;
-  int variant = 0;  // PA gradient-apply tile configuration, see kVariants
+  int ctas_per_sm = 2;
+  int variant = 1;  // PA gradient-apply tile configuration, see kVariants
 };
 
 static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((nelems * 8 + threads - 1) / threads); }

@@ -190,6 +190,35 @@ __global__ void k_plane_pack(const double* __restrict__ v, double* __restrict__ 
 static long g_host_launches = 0;
 static inline unsigned nb(long n) { ++g_host_launches; return (unsigned)((n + 255) / 256); }
 
+// ---------------------------------------------------------------- per-kernel timing ---------
+// CUDA-event pairs recorded on the launching stream around one kernel family; elapsed times are
+// harvested after the step (no host sync inside the hot loop).
+struct KernelTimer {
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  double total_ms = 0.0;
+  long count = 0;
+  bool enabled = false;
+  ~KernelTimer() { for (auto e : ev) cudaEventDestroy(e); }
+  void Begin(cudaStream_t s) {
+    if (!enabled || used + 2 > 8192) return;
+    if (used + 2 > ev.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); }
+    cudaEventRecord(ev[used], s);
+  }
+  void End(cudaStream_t s) {
+    if (!enabled || used + 2 > 8192 || used + 2 > ev.size()) return;
+    cudaEventRecord(ev[used + 1], s);
+    used += 2;
+  }
+  void Harvest() {  // stream must be synchronised
+    for (size_t i = 0; i + 1 < used; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) { total_ms += ms; ++count; }
+    }
+    used = 0;
+  }
+};
+
 // ---------------------------------------------------------------- communicator --------------
 class SlabComm {
  public:
@@ -325,7 +354,7 @@ class NonlinearMechOperator : public Operator {
   mutable GradientOperator jacobian;
   Vector ess_mask_dev;           // device copy of the per-node essential mask (bytes)
   mutable long grad_mults = 0, residuals = 0;
-  mutable double t_setup = 0, t_model = 0;
+  mutable KernelTimer tm_grad_mult, tm_model_setup;
 
   NonlinearMechOperator(exab200_ctx* c, SlabComm* cm, cudaStream_t s, ExaModel* m, long ne, long nn, Vector* xb)
       : ctx(c), comm(cm), stream(s), model(m), nelems(ne), nnodes(nn), x_beg(xb), el_jac(ne * 72), diag(3 * nn), jacobian(this) {}
@@ -337,7 +366,9 @@ class NonlinearMechOperator : public Operator {
   template <bool upd_crds>
   void Setup(const Vector& k) const {
     XCK(exab200_setup_jacobians(ctx, x_beg->Read(), upd_crds ? k.Read() : nullptr, model->dt, el_jac.Write(), stream));
+    tm_model_setup.Begin(stream);
     model->ModelSetup(8, (int)nelems, 3, 8, el_jac, el_jac /*shape gradients are analytic in-kernel*/, k);
+    tm_model_setup.End(stream);
   }
   // src/mechanics_operator.cpp:288-308: y = H(k)
   void Mult(const Vector& k, Vector& y) const override {
@@ -371,7 +402,9 @@ class NonlinearMechOperator : public Operator {
 };
 
 void GradientOperator::Mult(const Vector& x, Vector& y) const {
+  op->tm_grad_mult.Begin(op->stream);
   XCK(exab200_grad_mult(op->ctx, x.Read(), y.Write(), 0, op->stream));
+  op->tm_grad_mult.End(op->stream);
   op->comm->HaloSum(y.Write());
   ++op->grad_mults;
 }
@@ -542,6 +575,7 @@ struct exahost_sim {
   std::unique_ptr<CGSolver> cg;
   std::unique_ptr<ExaNewtonSolver> newton;
   double* h_pinned = nullptr;  // staging for host-buffer steps
+  cudaEvent_t ev[4];
   long newton_total = 0;
 
   // SystemDriver::UpdateVelocity (src/system_driver.cpp:327-333)
@@ -670,6 +704,7 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
     s->newton->smoother = s->smoother.get();
     s->newton->print_level = cfg->verbose ? 0 : -1;
     HCK(cudaMallocHost(&s->h_pinned, sizeof(double) * n));
+    for (int i = 0; i < 4; ++i) HCK(cudaEventCreate(&s->ev[i]));
     *out = s;
     return 0;
   } catch (const Abort& a) {
@@ -706,17 +741,20 @@ int exahost_set_bcs(exahost_sim* s, const unsigned char* mask, const double* h_e
 //   bc_changed: run the SolveInit corrector first (src/mechanics_driver.cpp:866-878)
 //   h_ess_val_in  (may be NULL): prescribed velocities for this step, HOST buffer, copied H2D inside the call
 //   h_vel_out     (may be NULL): converged velocity, HOST buffer, copied D2H inside the call
-//   out: {newton_iters, pcg_iters, converged, model_setups, grad_mults, seconds, avg_stress[6]}
+//   out[16]: {newton_iters, pcg_iters, converged, model_setups, grad_mults, wall seconds, avg_stress[6],
+//             device ms of the solve (CUDA events, copies excluded), device ms end to end (copies included)}
 int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out, double* out) {
   try {
     HCK(cudaSetDevice(s->cfg.device));
     const long n = 3 * s->nnodes;
     auto t0 = std::chrono::steady_clock::now();
     const long pcg0 = s->cg->total_iters, ms0 = s->model->model_setups, gm0 = s->oper->grad_mults;
+    HCK(cudaEventRecord(s->ev[0], s->stream));
     if (h_ess_val_in) {
       std::memcpy(s->h_pinned, h_ess_val_in, sizeof(double) * n);
       HCK(cudaMemcpyAsync(s->ess_val.d, s->h_pinned, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
     }
+    HCK(cudaEventRecord(s->ev[1], s->stream));
     s->model->SetModelDt(dt);
     if (bc_changed) {
       HCK(cudaMemcpyAsync(s->v_prev.d, s->v_sol.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
@@ -733,13 +771,22 @@ int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_
     s->UpdateModel(avg);
     // x_beg = x_cur (src/mechanics_driver.cpp:907): x_beg += dt * v
     k_axpby<<<nb(n), 256, 0, s->stream>>>(s->x_beg.d, s->v_sol.d, dt, 1.0, n);
+    HCK(cudaEventRecord(s->ev[2], s->stream));
     if (h_vel_out) {
       HCK(cudaMemcpyAsync(s->h_pinned, s->v_sol.d, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
       HCK(cudaStreamSynchronize(s->stream));
       std::memcpy(h_vel_out, s->h_pinned, sizeof(double) * n);
     }
+    HCK(cudaEventRecord(s->ev[3], s->stream));
     HCK(cudaStreamSynchronize(s->stream));
     auto t1 = std::chrono::steady_clock::now();
+    s->oper->tm_grad_mult.Harvest();
+    s->oper->tm_model_setup.Harvest();
+    float ms_dev = 0.f, ms_e2e = 0.f;
+    HCK(cudaEventElapsedTime(&ms_dev, s->ev[1], s->ev[2]));
+    HCK(cudaEventElapsedTime(&ms_e2e, s->ev[0], s->ev[3]));
+    out[12] = ms_dev;
+    out[13] = ms_e2e;
     s->newton_total += s->newton->final_iter;
     out[0] = s->newton->final_iter;
     out[1] = (double)(s->cg->total_iters - pcg0);
@@ -776,6 +823,20 @@ long exahost_counter(exahost_sim* s, int which) {
   }
   return -1;
 }
+
+// per-kernel CUDA-event timing: which = 0 gradient apply (memset + kernel), 1 material update
+int exahost_kernel_timing(exahost_sim* s, int enable) {
+  s->oper->tm_grad_mult.enabled = s->oper->tm_model_setup.enabled = enable != 0;
+  return 0;
+}
+int exahost_kernel_time(exahost_sim* s, int which, double* total_ms, long* count, int reset) {
+  KernelTimer& t = which == 0 ? s->oper->tm_grad_mult : s->oper->tm_model_setup;
+  *total_ms = t.total_ms;
+  *count = t.count;
+  if (reset) { t.total_ms = 0.0; t.count = 0; }
+  return 0;
+}
+int exahost_set_tuning(exahost_sim* s, int ctas_per_sm, int variant) { return exab200_set_tuning(s->ctx, ctas_per_sm, variant); }
 
 void* exahost_stream(exahost_sim* s) { return s->stream; }
 void* exahost_ctx(exahost_sim* s) { return s->ctx; }

@@ -115,12 +115,13 @@ class VoxelSim:
         return mask, val
 
     def step(self, dt, bc_changed=False, ess_val_host=None, vel_out_host=None):
-        out = np.zeros(12)
+        out = np.zeros(16)
         pin = ess_val_host.ctypes.data_as(C.c_void_p) if ess_val_host is not None else None
         pout = vel_out_host.ctypes.data_as(C.c_void_p) if vel_out_host is not None else None
         _chk(lib().exahost_step(self._h, C.c_double(dt), int(bc_changed), pin, pout, out.ctypes.data_as(C.c_void_p)))
         return dict(newton_iters=int(out[0]), pcg_iters=int(out[1]), converged=bool(out[2]), model_setups=int(out[3]),
-                    grad_mults=int(out[4]), seconds=float(out[5]), avg_stress=out[6:12].copy())
+                    grad_mults=int(out[4]), seconds=float(out[5]), avg_stress=out[6:12].copy(),
+                    dev_ms=float(out[12]), e2e_ms=float(out[13]))
 
     def get(self, which):
         sizes = {"stress": self.nelems * 48, "hist": self.nelems * 8 * self.nstatev, "vel": 3 * self.nnodes,
@@ -134,6 +135,17 @@ class VoxelSim:
         idx = {"launches": 0, "allreduces": 1, "halos": 2, "model_setups": 3, "grad_mults": 4, "pcg_iters": 5,
                "newton_iters": 6}[name]
         return lib().exahost_counter(self._h, idx)
+
+    def kernel_timing(self, enable=True):
+        lib().exahost_kernel_timing(self._h, int(enable))
+
+    def kernel_time(self, which, reset=False):
+        tot, cnt = C.c_double(0), C.c_long(0)
+        lib().exahost_kernel_time(self._h, {"grad_mult": 0, "model_setup": 1}[which], C.byref(tot), C.byref(cnt), int(reset))
+        return tot.value, cnt.value
+
+    def set_tuning(self, ctas_per_sm, variant):
+        _chk(lib().exahost_set_tuning(self._h, ctas_per_sm, variant))
 
     def run(self, dts, bcs):
         """The reference's time loop (src/mechanics_driver.cpp:837-907). bcs: list of (step, ids, comps, vals)."""

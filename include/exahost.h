@@ -43,7 +43,10 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out);
 void exahost_destroy(exahost_sim* sim);
 int exahost_set_bcs(exahost_sim* sim, const unsigned char* mask_per_node, const double* h_ess_val_L);
 int exahost_step(exahost_sim* sim, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out,
-                 double* out12);
+                 double* out16);
+int exahost_kernel_timing(exahost_sim* sim, int enable);
+int exahost_kernel_time(exahost_sim* sim, int which, double* total_ms, long* count, int reset);
+int exahost_set_tuning(exahost_sim* sim, int ctas_per_sm, int variant);
 int exahost_get(exahost_sim* sim, int which, double* h_out);
 long exahost_counter(exahost_sim* sim, int which);
 void* exahost_stream(exahost_sim* sim);

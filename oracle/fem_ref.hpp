@@ -82,6 +82,7 @@ inline void voxel_mesh(int nx, int ny, int nz, double lx, double ly, double lz,
 // L-vector (byNODES) -> E-vector, ElementRestriction::Mult with NATIVE
 // ordering (src/mechanics_operator.cpp:345, src/mechanics_operator_ext.cpp:150).
 inline void gather(long ne, long nn, const int* e2n, const double* xL, double* xE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int i = 0; i < 3; ++i)
       for (int a = 0; a < 8; ++a) xE[e * 24 + i * 8 + a] = xL[i * nn + e2n[e * 8 + a]];
@@ -90,9 +91,13 @@ inline void gather(long ne, long nn, const int* e2n, const double* xL, double* x
 // E-vector -> L-vector scatter-add, ElementRestriction::MultTranspose
 // (src/mechanics_operator_ext.cpp:156).  yL must be zeroed by the caller.
 inline void scatter_add(long ne, long nn, const int* e2n, const double* yE, double* yL) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int i = 0; i < 3; ++i)
-      for (int a = 0; a < 8; ++a) yL[i * nn + e2n[e * 8 + a]] += yE[e * 24 + i * 8 + a];
+      for (int a = 0; a < 8; ++a) {
+#pragma omp atomic
+        yL[i * nn + e2n[e * 8 + a]] += yE[e * 24 + i * 8 + a];
+      }
 }
 
 // Jacobians at the quadrature points from nodal coordinates in E-vector form.
@@ -100,6 +105,7 @@ inline void scatter_add(long ne, long nn, const int* e2n, const double* yE, doub
 // NonlinearMechOperator::SetupJacobianTerms (src/mechanics_operator.cpp:350-391):
 // J(i,s,q,e) = sum_a X(a,i,e) G(a,s,q).
 inline void jacobians(long ne, const double* G, const double* xE, double* jac) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q)
       for (int s = 0; s < 3; ++s)
@@ -133,6 +139,7 @@ inline double adjugate(const double* Jq, double* adj) {
 // exaconstit::kernel::grad_calc (src/mechanics_kernels.cpp:7-78).
 // grad(i,t,q,e) -> out[(e*8+q)*9 + t*3 + i]; accumulates (+=) like the reference.
 inline void grad_calc(long ne, const double* jac, const double* G, const double* xE, double* out) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -151,6 +158,7 @@ static const int kVoigt[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
 
 // ExaModel::TransformMatGradTo4D (src/mechanics_model.cpp:949-1061).
 inline void transform_matgrad_4d(long npts, const double* k36, double* c81) {
+#pragma omp parallel for schedule(static)
   for (long p = 0; p < npts; ++p)
     for (int l = 0; l < 3; ++l)
       for (int k = 0; k < 3; ++k)
@@ -163,6 +171,7 @@ inline void transform_matgrad_4d(long npts, const double* k36, double* c81) {
 // ExaNLFIntegrator::AssemblePA (src/mechanics_integrators.cpp:240-312):
 // Dres(j,k,q,e) = W_q sum_m adj(J)(j,m) sigma(m,k) -> d[((e*8+q)*3 + k)*3 + j].
 inline void assemble_pa(long ne, const double* jac, const double* W, const double* stress, double* d) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -181,6 +190,7 @@ inline void assemble_pa(long ne, const double* jac, const double* W, const doubl
 
 // ExaNLFIntegrator::AddMultPA (src/mechanics_integrators.cpp:545-555).
 inline void addmult_pa(long ne, const double* G, const double* d, double* yE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q)
       for (int k = 0; k < 3; ++k)
@@ -193,6 +203,7 @@ inline void addmult_pa(long ne, const double* G, const double* d, double* yE) {
 // A(r,c) = adj(J)(c,r); D(e,q,i,k,l,n) = (dt W/detJ) sum_{j,m} A(j,i) C(j,k,l,m) A(m,n).
 inline void assemble_grad_pa(long ne, double dt, const double* jac, const double* W,
                              const double* c81, double* D) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -217,6 +228,7 @@ inline void assemble_grad_pa(long ne, double dt, const double* jac, const double
 
 // ExaNLFIntegrator::AddMultGradPA (src/mechanics_integrators.cpp:592-620).
 inline void addmult_grad_pa(long ne, const double* G, const double* D, const double* xE, double* yE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       const double* Dq = &D[(e * 8 + q) * 81];
@@ -245,6 +257,7 @@ inline void bvec(const double* G, const double* adj, int q, int a, double* b) {
 // ExaNLFIntegrator::AssembleGradDiagonalPA (src/mechanics_integrators.cpp:668-746).
 inline void assemble_grad_diag_pa(long ne, double dt, const double* jac, const double* W,
                                   const double* G, const double* k36, double* dE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -272,6 +285,7 @@ inline void assemble_grad_diag_pa(long ne, double dt, const double* jac, const d
 // E(l+8I, k+8Kc, e) += c * sum_{p,r} g_p(l) K(v(I,p), v(Kc,r)) b_r(k).
 inline void assemble_ea(long ne, double dt, const double* jac, const double* W, const double* G,
                         const double* k36, double* ea) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -305,6 +319,7 @@ inline void assemble_ea(long ne, double dt, const double* jac, const double* W, 
 // EANonlinearMechOperatorGradExt::TMult inner loop
 // (src/mechanics_operator_ext.cpp:303-314): Y(j,e) += sum_i A(i,j,e) X(i,e).
 inline void ea_mult(long ne, const double* ea, const double* xE, double* yE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int j = 0; j < 24; ++j) {
       double res = 0.0;
@@ -315,6 +330,7 @@ inline void ea_mult(long ne, const double* ea, const double* xE, double* yE) {
 
 // EA AssembleDiagonal element part (src/mechanics_operator_ext.cpp:246-252).
 inline void ea_diag(long ne, const double* ea, double* dE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int j = 0; j < 24; ++j) dE[e * 24 + j] = ea[e * 576 + j * 24 + j];
 }
@@ -323,6 +339,7 @@ inline void ea_diag(long ne, const double* ea, double* dE) {
 // ICExaNLFIntegrator::AssemblePA element-average shape gradients
 // (src/mechanics_integrators.cpp:1895-1952): eDS(a,c,e) -> eds[e*24 + c*8 + a].
 inline void ic_assemble_eds(long ne, const double* jac, const double* W, const double* G, double* eds) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e) {
     double vol = 0.0;
     for (int x = 0; x < 24; ++x) eds[e * 24 + x] = 0.0;
@@ -360,6 +377,7 @@ inline void bbar_block(const double* G, const double* adj, double idetJ, const d
 // ICExaNLFIntegrator::AddMultPA (src/mechanics_integrators.cpp:2011-2085).
 inline void ic_addmult_pa(long ne, const double* jac, const double* W, const double* G,
                           const double* eds, const double* stress, double* yE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -382,6 +400,7 @@ inline void ic_addmult_pa(long ne, const double* jac, const double* W, const dou
 // E(l+8I, k+8Kc, e) += dt W detJ * sum_{R,S} Bbar_l(R,I) K(R,S) Bbar_k(S,Kc).
 inline void ic_assemble_ea(long ne, double dt, const double* jac, const double* W, const double* G,
                            const double* eds, const double* k36, double* ea) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -414,6 +433,7 @@ inline void ic_assemble_ea(long ne, double dt, const double* jac, const double* 
 inline void ic_assemble_grad_diag_pa(long ne, double dt, const double* jac, const double* W,
                                      const double* G, const double* eds, const double* k36,
                                      double* dE) {
+#pragma omp parallel for schedule(static)
   for (long e = 0; e < ne; ++e)
     for (int q = 0; q < 8; ++q) {
       double adj[9];
@@ -440,14 +460,28 @@ inline void ic_assemble_grad_diag_pa(long ne, double dt, const double* jac, cons
 inline void vol_sum(long ne, int vdim, const double* jac, const double* W, const double* qf,
                     double* sums, double* vol) {
   for (int c = 0; c < vdim; ++c) sums[c] = 0.0;
-  *vol = 0.0;
-  for (long e = 0; e < ne; ++e)
-    for (int q = 0; q < 8; ++q) {
-      double adj[9];
-      const double w = adjugate(&jac[(e * 8 + q) * 9], adj) * W[q];
-      *vol += w;
-      for (int c = 0; c < vdim; ++c) sums[c] += w * qf[(e * 8 + q) * vdim + c];
+  double v = 0.0;
+  std::vector<double> acc(vdim, 0.0);
+#pragma omp parallel
+  {
+    std::vector<double> loc(vdim, 0.0);
+    double lv = 0.0;
+#pragma omp for schedule(static) nowait
+    for (long e = 0; e < ne; ++e)
+      for (int q = 0; q < 8; ++q) {
+        double adj[9];
+        const double w = adjugate(&jac[(e * 8 + q) * 9], adj) * W[q];
+        lv += w;
+        for (int c = 0; c < vdim; ++c) loc[c] += w * qf[(e * 8 + q) * vdim + c];
+      }
+#pragma omp critical
+    {
+      v += lv;
+      for (int c = 0; c < vdim; ++c) acc[c] += loc[c];
     }
+  }
+  *vol = v;
+  for (int c = 0; c < vdim; ++c) sums[c] = acc[c];
 }
 
 }  // namespace orc
