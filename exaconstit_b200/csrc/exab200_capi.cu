@@ -31,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct exab200_ctx {
   exab200_config cfg;
   MatDev mat;
+  MatDev* d_mat = nullptr;  // device copy read by K1
   int device = 0, sm_count = 148;
   int* d_e2n = nullptr;
   unsigned char* d_ess = nullptr;
@@ -43,7 +44,7 @@ struct exab200_ctx {
   double* d_ea = nullptr;  // EA element matrices (assembly == EA)
   long launches = 0;
   int ctas_per_sm = 2;
-  int variant = 1;  // PA gradient-apply tile configuration, see kVariants
+  int variant = 10;  // PA gradient-apply tile configuration, see kVariants
 };
 
 static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((nelems * 8 + threads - 1) / threads); }
@@ -75,14 +76,38 @@ static int launch_gm(exab200_ctx* c, const double* x, double* y, ElemIO io, cuda
   POST_LAUNCH(c);
   return 0;
 }
+template <int NW, int STAGES, int MODE, bool ESS>
+static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
+  constexpr int smem = NW * STAGES * kWarpStageBytes + NW * STAGES * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_grad_mult_pa_w<NW, STAGES, MODE, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long nwt = (c->cfg.nelems + 3) / 4;
+  long grid = (long)c->sm_count * c->ctas_per_sm;
+  if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
+  k_grad_mult_pa_w<NW, STAGES, MODE, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->d_matgrad, c->d_jac, x, y, io,
+                                                                                  c->cfg.nelems, c->grad_dt);
+  POST_LAUNCH(c);
+  return 0;
+}
 template <int MODE, bool ESS>
 static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
   switch (c->variant) {
+    case 0: return launch_gm<16, 4, MODE, ESS>(c, x, y, io, st);
     case 1: return launch_gm<16, 2, MODE, ESS>(c, x, y, io, st);
     case 2: return launch_gm<32, 2, MODE, ESS>(c, x, y, io, st);
     case 3: return launch_gm<8, 4, MODE, ESS>(c, x, y, io, st);
     case 4: return launch_gm<16, 3, MODE, ESS>(c, x, y, io, st);
-    default: return launch_gm<16, 4, MODE, ESS>(c, x, y, io, st);
+    // warp-private pipelines {warps per CTA, stages}
+    case 10: return launch_gmw<4, 2, MODE, ESS>(c, x, y, io, st);
+    case 11: return launch_gmw<4, 3, MODE, ESS>(c, x, y, io, st);
+    case 12: return launch_gmw<8, 2, MODE, ESS>(c, x, y, io, st);
+    case 13: return launch_gmw<2, 3, MODE, ESS>(c, x, y, io, st);
+    case 14: return launch_gmw<4, 4, MODE, ESS>(c, x, y, io, st);
+    case 15: return launch_gmw<3, 3, MODE, ESS>(c, x, y, io, st);
+    default: return launch_gmw<4, 2, MODE, ESS>(c, x, y, io, st);
   }
 }
 
@@ -157,6 +182,8 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
     CK(cudaMalloc(&c->d_ess, cfg->nnodes));
     CK(cudaMemset(c->d_ess, 0, cfg->nnodes));
   }
+  CK(cudaMalloc(&c->d_mat, sizeof(MatDev)));
+  CK(cudaMemcpy(c->d_mat, &c->mat, sizeof(MatDev), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_fail, sizeof(int)));
   CK(cudaMemset(c->d_fail, 0, sizeof(int)));
   if (cfg->assembly == EXAB200_EA) CK(cudaMalloc(&c->d_ea, sizeof(double) * 576 * cfg->nelems));
@@ -170,6 +197,7 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_e2n);
   cudaFree(c->d_ess);
   cudaFree(c->d_fail);
+  cudaFree(c->d_mat);
   cudaFree(c->d_ea);
   delete c;
 }
@@ -177,7 +205,7 @@ void exab200_destroy(exab200_ctx* c) {
 int exab200_num_state_vars(const exab200_ctx* c) { return c ? c->mat.nhist : -1; }
 long exab200_launch_count(const exab200_ctx* c) { return c ? c->launches : -1; }
 int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
-  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8 || variant < 0 || variant > 4) return fail("bad tuning");
+  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8 || variant < 0 || variant > 15) return fail("bad tuning");
   c->ctas_per_sm = ctas_per_sm;
   c->variant = variant;
   return 0;
@@ -226,14 +254,14 @@ static int model_setup_impl(exab200_ctx* c, int mode, double dt, const double* d
   const long ne = c->cfg.nelems, nn = c->cfg.nnodes;
   if (c->mat.nslip == 12) {
     if (mode == LVEC)
-      k_model_setup<12, LVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+      k_model_setup<12, LVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
     else
-      k_model_setup<12, EVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+      k_model_setup<12, EVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
   } else {
     if (mode == LVEC)
-      k_model_setup<24, LVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+      k_model_setup<24, LVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
     else
-      k_model_setup<24, EVEC><<<nb, 128, 0, st>>>(c->mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
+      k_model_setup<24, EVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
   }
   POST_LAUNCH(c);
   return 0;

@@ -37,6 +37,7 @@ struct MatDev {
   double tol, gruneisen, dtde, tK0;
   // Voce power law
   double xm, gam_w0, h0, tausi, taus0, xmprime, xms, gamss0, kappa0;
+  double pl_t_min, pl_t_max, pl_max, ln_ovf;  // power-law guards, precomputed on the host
   // KMBalD
   double mu_ref, tau_a, p_exp, q_exp, gam_wo, gam_ro, wrD, k1, k2o, ninv, gamma_o, rho_dd_init;
   double c_1[kMaxSlip], go[kMaxSlip], s_[kMaxSlip];
@@ -143,20 +144,18 @@ __device__ __forceinline__ void exp_Jr(const double* xi, double Jm[3][3]) {
 }
 
 // ---- kinetics ---------------------------------------------------------------------------
-__device__ __forceinline__ void kin_power_law(double gam_w, double xm, double g, double tau, double& gdot,
+__device__ __forceinline__ void kin_power_law(const MatDev& m, double gam_w, double g, double tau, double& gdot,
                                               double& dgdot_dtau) {
   gdot = 0.0;
   dgdot_dtau = 0.0;
-  const double xmi = 1.0 / xm;
-  const double t_min = pow(gam_ratio_min, xm), t_max = pow(gam_ratio_ovf, xm);
+  const double xmi = 1.0 / m.xm;
   const double gi = 1.0 / g;
   const double t = tau * gi, at = fabs(t);
-  if (at <= t_min) return;
-  if (at > t_max) {
-    const double pl = exp((xmi - 1.0) * log(t_max));
-    const double d = gam_w * pl * xmi * gi;
-    const double g0 = gam_w * t_max * pl;
-    gdot = (g0 + d * g * (at - t_max)) * (t > 0 ? 1.0 : -1.0);
+  if (at <= m.pl_t_min) return;
+  if (at > m.pl_t_max) {  // linear extrapolation beyond the overflow guard
+    const double d = gam_w * m.pl_max * xmi * gi;
+    const double g0 = gam_w * m.pl_t_max * m.pl_max;
+    gdot = (g0 + d * g * (at - m.pl_t_max)) * (t > 0 ? 1.0 : -1.0);
     dgdot_dtau = d;
     return;
   }
@@ -186,18 +185,19 @@ __device__ __forceinline__ void kin_kmbald(const MatDev& m, double g, double gam
   if (at_0 >= 1.0) {
     const double xn = c_e * m.p_exp;
     const double lg = xn * log(at_0);
-    if (lg > log(gam_ratio_ovf)) { gdot = sgn * gdot_r; dgdot_dtau = dgdot_r; return; }
+    if (lg > m.ln_ovf) { gdot = sgn * gdot_r; dgdot_dtau = dgdot_r; return; }
     gdot_w = gam_w * exp(lg);
     dgdot_w = gdot_w * xn / at_0 * g_i;
   } else {
-    const double pf = pow(at_0, m.p_exp);
-    const double dpf = m.p_exp * pow(at_0, m.p_exp - 1.0) * g_i;
+    const bool p1 = m.p_exp == 1.0, q1 = m.q_exp == 1.0;
+    const double pf = p1 ? at_0 : pow(at_0, m.p_exp);
+    const double dpf = p1 ? g_i : m.p_exp * pow(at_0, m.p_exp - 1.0) * g_i;
     const double qa = 1.0 - pf;
-    const double ef = exp(-c_e * pow(qa, m.q_exp));
-    const double dqf = m.q_exp * pow(qa, m.q_exp - 1.0) * dpf;
+    const double ef = exp(-c_e * (q1 ? qa : pow(qa, m.q_exp)));
+    const double dqf = q1 ? dpf : m.q_exp * pow(qa, m.q_exp - 1.0) * dpf;
     const double qb = 1.0 + pf;
-    const double eb = exp(-c_e * pow(qb, m.q_exp));
-    const double dqb = m.q_exp * pow(qb, m.q_exp - 1.0) * dpf;
+    const double eb = exp(-c_e * (q1 ? qb : pow(qb, m.q_exp)));
+    const double dqb = q1 ? dpf : m.q_exp * pow(qb, m.q_exp - 1.0) * dpf;
     gdot_w = gam_w * (ef - eb);
     dgdot_w = gam_w * c_e * (ef * dqf + eb * dqb);
     if (gdot_w <= gam_ratio_min * gam_w) return;
@@ -241,7 +241,7 @@ __device__ __forceinline__ double kin_update_h(const MatDev& m, double h_n, doub
 }
 
 // ---- dense LU (n = 8) with partial pivoting on a local array ------------------------------
-__device__ inline bool lu_factor8(double* A, int* piv) {
+__device__ __noinline__ bool lu_factor8(double* A, int* piv) {
   for (int k = 0; k < 8; ++k) {
     int p = k;
     double mx = fabs(A[k * 8 + k]);
@@ -262,7 +262,7 @@ __device__ inline bool lu_factor8(double* A, int* piv) {
   }
   return true;
 }
-__device__ inline void lu_solve8(const double* A, const int* piv, double* b) {
+__device__ __noinline__ void lu_solve8(const double* A, const int* piv, double* b) {
   // rows of L were swapped in full during factorisation: apply every interchange first
   for (int k = 0; k < 8; ++k) {
     const int p = piv[k];
@@ -283,28 +283,31 @@ struct Problem {
   double dt, dt_ri, detVi, tK;
   double e_n[5], q_n[4], d_sm[5], w_sm[3];
   double eps_si, rot_si;
-  double g[NSLIP], c_e[NSLIP], gam_w, gam_r;
+  static constexpr int NG = (NSLIP == 24) ? 24 : 1;  // per-system resistances only differ for HCP families
+  double g[NG], c_e[NG], gam_w, gam_r;
   // state of the last evaluation
   double e_f[5], q_f[4], C[9];
   double shrate, disRate;
+  double gdot[NSLIP];
+  __device__ __forceinline__ double gv(int a) const { return g[NG == 1 ? 0 : a]; }
+  __device__ __forceinline__ double cev(int a) const { return c_e[NG == 1 ? 0 : a]; }
 
   __device__ void kin_vals(const MatDev& m, double h) {
     if (m.kin == KIN_KMBALD) {
       const double sq = exp(0.5 * h);
-#pragma unroll
-      for (int a = 0; a < NSLIP; ++a) { g[a] = m.go[a] + m.s_[a] * sq; c_e[a] = m.c_1[a] / tK * m.mu_ref; }
+      for (int a = 0; a < NG; ++a) { g[a] = m.go[a] + m.s_[a] * sq; c_e[a] = m.c_1[a] / tK * m.mu_ref; }
       gam_w = m.gam_wo / sq;
       gam_r = m.gam_ro * sq * sq;
     } else {
-#pragma unroll
-      for (int a = 0; a < NSLIP; ++a) g[a] = h;
+      for (int a = 0; a < NG; ++a) { g[a] = h; c_e[a] = 0.0; }
       gam_w = m.gam_w0;
       gam_r = 0.0;
     }
   }
 
-  // residual R[8]; if Jac != nullptr also the 8x8 Jacobian (row-major); gdot_out optional
-  __device__ void eval(const MatDev& m, const double* x, double* R, double* Jac, double* gdot_out) {
+  // residual R[8]; if Jac != nullptr also the 8x8 Jacobian (row-major).  Deliberately not inlined: one
+  // copy of this body keeps the kernel inside the instruction cache.
+  __device__ __noinline__ void eval(const MatDev& m, const double* x, double* R, double* Jac) {
     double edot[5], xi[3];
 #pragma unroll
     for (int i = 0; i < 5; ++i) { const double de = e_scale * x[i]; e_f[i] = e_n[i] + de; edot[i] = de * dt_ri; }
@@ -349,15 +352,15 @@ struct Problem {
     }
     shrate = 0.0;
     disRate = 0.0;
-#pragma unroll 4
+#pragma unroll 1
     for (int a = 0; a < NSLIP; ++a) {
       double tau = 0.0;
 #pragma unroll
       for (int i = 0; i < 5; ++i) tau += m.P[a][i] * T[i];
       double gd, dg;
-      if (m.kin == KIN_KMBALD) kin_kmbald(m, g[a], gam_w, gam_r, c_e[a], tau, gd, dg);
-      else kin_power_law(gam_w, m.xm, g[a], tau, gd, dg);
-      if (gdot_out) gdot_out[a] = gd;
+      if (m.kin == KIN_KMBALD) kin_kmbald(m, gv(a), gam_w, gam_r, cev(a), tau, gd, dg);
+      else kin_power_law(m, gam_w, gv(a), tau, gd, dg);
+      gdot[a] = gd;
       shrate += fabs(gd);
       disRate += tau * gd;
 #pragma unroll
@@ -443,11 +446,13 @@ __device__ __forceinline__ double norm8(const double* v) {
 }
 
 // trust-region dogleg Newton; returns number of residual evaluations, negative on failure.
-// On return R/J hold the residual and Jacobian at the returned x.
+// On return R/J hold the residual and (unfactored) Jacobian at the returned x.  The Jacobian is
+// factored in place: grad = J^T R and J grad are formed first, and the linear model of any dogleg
+// step s = -a grad + b nr follows from J nr = -R as  R + J s = (1 - b) R - a (J grad).
 template <int NSLIP>
-__device__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, double* x, double* R, double* J, double tol) {
+__device__ __noinline__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, double* x, double* R, double* J, double tol) {
   double Rt[8], xt[8];
-  prob.eval(m, x, R, J, nullptr);
+  prob.eval(m, x, R, J);
   int nfev = 1;
   double res = norm8(R);
   double delta = 1.0e2;
@@ -455,29 +460,27 @@ __device__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, double* x, doub
   const double deltaMin = 1e-12, deltaMax = 1e4;
   for (int it = 0; it < 200; ++it) {
     if (res <= tol) return nfev;
-    double grad[8], Jg[8], nr[8], Jc[64];
+    double grad[8], Jg[8], nr[8];
     int piv[8];
     for (int j = 0; j < 8; ++j) { double s = 0; for (int i = 0; i < 8; ++i) s += J[i * 8 + j] * R[i]; grad[j] = s; }
     for (int i = 0; i < 8; ++i) { double s = 0; for (int j = 0; j < 8; ++j) s += J[i * 8 + j] * grad[j]; Jg[i] = s; }
-    for (int i = 0; i < 64; ++i) Jc[i] = J[i];
     for (int i = 0; i < 8; ++i) nr[i] = -R[i];
-    const bool have_newton = lu_factor8(Jc, piv);
-    if (have_newton) lu_solve8(Jc, piv, nr);
+    const bool have_newton = lu_factor8(J, piv);
+    if (have_newton) lu_solve8(J, piv, nr);
     double g2 = 0, Jg2 = 0;
     for (int i = 0; i < 8; ++i) { g2 += grad[i] * grad[i]; Jg2 += Jg[i] * Jg[i]; }
+    const double nrn = have_newton ? norm8(nr) : 1e300;
     bool accepted = false;
     while (!accepted) {
-      double step[8], pred;
-      const double nrn = have_newton ? norm8(nr) : 1e300;
+      double ca, cb, pred;  // step = -ca * grad + cb * nr
       if (have_newton && nrn <= delta) {
-        for (int i = 0; i < 8; ++i) step[i] = nr[i];
+        ca = 0.0; cb = 1.0;
         pred = res;
       } else {
         const double alpha = (Jg2 > 0) ? g2 / Jg2 : 0.0;
         const double cpn = alpha * sqrt(g2);
         if (cpn >= delta || !have_newton) {
-          const double f = delta / sqrt(g2 > 0 ? g2 : 1.0);
-          for (int i = 0; i < 8; ++i) step[i] = -f * grad[i];
+          ca = delta / sqrt(g2 > 0 ? g2 : 1.0); cb = 0.0;
         } else {
           double a = 0, b = 0, c = -delta * delta;
           for (int i = 0; i < 8; ++i) {
@@ -485,34 +488,36 @@ __device__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, double* x, doub
             a += d * d; b += 2.0 * cp * d; c += cp * cp;
           }
           const double beta = (-b + sqrt(fmax(0.0, b * b - 4 * a * c))) / (2 * a);
-          for (int i = 0; i < 8; ++i) { const double cp = -alpha * grad[i]; step[i] = cp + beta * (nr[i] - cp); }
+          ca = alpha * (1.0 - beta); cb = beta;
         }
-        double lin[8];
-        for (int i = 0; i < 8; ++i) { double s = R[i]; for (int j = 0; j < 8; ++j) s += J[i * 8 + j] * step[j]; lin[i] = s; }
-        pred = res - norm8(lin);
+        double l2 = 0.0;
+        for (int i = 0; i < 8; ++i) { const double l = (1.0 - cb) * R[i] - ca * Jg[i]; l2 += l * l; }
+        pred = res - sqrt(l2);
       }
-      for (int i = 0; i < 8; ++i) xt[i] = x[i] + step[i];
-      prob.eval(m, xt, Rt, nullptr, nullptr);
+      double sn = 0.0;
+      for (int i = 0; i < 8; ++i) { const double st = cb * nr[i] - ca * grad[i]; xt[i] = x[i] + st; sn += st * st; }
+      sn = sqrt(sn);
+      prob.eval(m, xt, Rt, nullptr);
       ++nfev;
       const double rest = norm8(Rt);
       const bool finite = isfinite(rest);
       const double rho = (finite && pred > 0) ? (res - rest) / pred : -1.0;
-      const double sn = norm8(step);
       if (finite && rest < res) {
         accepted = true;
         for (int i = 0; i < 8; ++i) x[i] = xt[i];
         if (rho > xiLG && sn >= 0.99 * delta) delta = fmin(deltaMax, delta * xiIncDelta);
         else if (rho < xiLO) delta = fmax(deltaMin, fmax(delta, sn) * xiDecDelta * 2.0);
-        prob.eval(m, x, R, J, nullptr);
+        prob.eval(m, x, R, J);
         ++nfev;
         res = norm8(R);
       } else {
         delta = fmin(delta, sn) * xiDecDelta;
-        if (delta < deltaMin) return -nfev;
+        if (delta < deltaMin) { prob.eval(m, x, R, J); return -(nfev + 1); }
       }
     }
   }
-  return (res <= tol) ? nfev : -nfev;
+  if (res > tol) return -nfev;
+  return nfev;
 }
 
 }  // namespace mat
@@ -524,14 +529,18 @@ __device__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, double* x, doub
 // src/mechanics_ecmech.cpp:159-169; TRANSPOSE=false reproduces the EA-on-device quirk, :155).
 // fail_count is incremented for points whose local solve did not converge.
 // ------------------------------------------------------------------------------------------
+#ifndef EXAB_K1_MIN_BLOCKS
+#define EXAB_K1_MIN_BLOCKS 2
+#endif
 template <int NSLIP, int MODE>
-__global__ void __launch_bounds__(128) k_model_setup(MatDev m, double dt, double temp_k, const double* __restrict__ jac,
+__global__ void __launch_bounds__(128, EXAB_K1_MIN_BLOCKS) k_model_setup(const MatDev* __restrict__ mp, double dt, double temp_k, const double* __restrict__ jac,
                                                      const double* __restrict__ vel, const int* __restrict__ e2n,
                                                      long nnodes, const double* __restrict__ stress0,
                                                      const double* __restrict__ hist0, double* __restrict__ stress1,
                                                      double* __restrict__ hist1, double* __restrict__ matgrad,
                                                      long nelems, int transpose, int* __restrict__ fail_count) {
   using namespace mat;
+  const MatDev& m = *mp;  // read-only, uniform across the grid (broadcast loads)
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 7;
   const long e = gt >> 3;
@@ -645,13 +654,11 @@ __global__ void __launch_bounds__(128) k_model_setup(MatDev m, double dt, double
   double x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, R[8], J[64];
   int nfev = solve_trdl<NSLIP>(m, prob, x, R, J, m.tol);
   if (nfev < 0) { atomicAdd(fail_count, 1); nfev = -nfev; }
-  double gdot[NSLIP];
-  prob.eval(m, x, R, J, gdot);
   // ---- history out (StateVarsSetup copy + updates + kernel_postprocessing) ----
   h1[iH_shrateEff] = prob.shrate;
   h1[iH_shrEff] = h0[iH_shrEff] + prob.shrate * dt;
   {
-    double flow = prob.g[0];
+    double flow = prob.gv(0);
     if (dEff > idp_tiny_sqrt) flow = prob.disRate / dEff;
     double plw = (dEff > idp_tiny_sqrt) ? flow * dEff * dt : 0.0;  // kernel_postprocessing :135-140
     h1[iH_flowStr] = plw + h0[iH_flowStr];
@@ -663,7 +670,7 @@ __global__ void __launch_bounds__(128) k_model_setup(MatDev m, double dt, double
   for (int i = 0; i < 4; ++i) h1[iH_Q + i] = prob.q_f[i];
   h1[iH_H] = h_u;
 #pragma unroll 4
-  for (int a = 0; a < NSLIP; ++a) h1[iH_Gdot + a] = gdot[a];
+  for (int a = 0; a < NSLIP; ++a) h1[iH_Gdot + a] = prob.gdot[a];
   h1[ind_vols] = vNew;
   // ---- stress out ----
   double sig_lat[5], sig_sm[5], s6[6];

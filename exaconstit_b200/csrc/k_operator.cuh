@@ -190,6 +190,160 @@ __global__ void __launch_bounds__(EPT * 8) k_grad_mult_pa(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// K2, warp-private pipelines (the default).  Same arithmetic as k_grad_mult_pa, but every warp owns
+// its own STAGES-deep ring of 4-element sub-tiles (4 x 2320 B skewed matGrad + 2304 B J per stage)
+// with its own mbarriers and refills a stage itself right after its last shared-memory read
+// (__syncwarp + proxy fence), so there is no CTA-wide barrier anywhere in the loop; the element
+// connectivity is prefetched two tiles ahead and the nodal values one tile ahead, so the
+// e2n -> x dependent-load chain never stalls the contraction.
+// ------------------------------------------------------------------------------------------
+constexpr int kWarpStageBytes = 4 * kCElemSmem + 4 * kJElemBytes;  // 11584
+
+template <int NW, int STAGES, int MODE, bool ESS>
+__global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __restrict__ matgrad,
+                                                            const double* __restrict__ jac,
+                                                            const double* __restrict__ x, double* __restrict__ y,
+                                                            ElemIO io, long nelems, double dt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
+  const int lane = l32 & 7;  // node / quadrature point
+  const int el = l32 >> 3;   // element slot in the warp's sub-tile
+  unsigned char* ring = smem_raw + (size_t)w * STAGES * kWarpStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NW * STAGES * kWarpStageBytes) + w * STAGES;
+  const long nwt = (nelems + 3) >> 2;                 // warp tiles
+  const long stride = (long)gridDim.x * NW;
+  const long wt0 = (long)blockIdx.x * NW + w;
+
+  if (l32 == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  auto issue = [&](long wt, int s) {
+    const long e0 = wt << 2;
+    const int ne = (int)min(4L, nelems - e0);
+    unsigned char* sc = ring + s * kWarpStageBytes;
+    if (l32 == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ne * (2 * kCHalfBytes + kJElemBytes));
+    __syncwarp();
+    if (l32 < 2 * ne) {
+      const int i = l32 >> 1, h = l32 & 1;
+      bulk_g2s(sc + i * kCElemSmem + h * (kCHalfBytes + 16),
+               reinterpret_cast<const unsigned char*>(matgrad + (e0 + i) * 288) + h * kCHalfBytes, kCHalfBytes, &full[s]);
+    } else if (l32 == 8) {
+      bulk_g2s(sc + 4 * kCElemSmem, jac + e0 * 72, (uint32_t)ne * kJElemBytes, &full[s]);
+    }
+  };
+  {
+    long t = wt0;
+    for (int s = 0; s < STAGES; ++s, t += stride)
+      if (t < nwt) issue(t, s);
+  }
+
+  auto load_nid = [&](long wt) -> long {
+    const long e = (wt << 2) + el;
+    if (wt >= nwt || e >= nelems) return -1;
+    if (MODE == LVEC) return io.e2n[e * 8 + lex_to_native(lane)];
+    return e * 24 + lex_to_native(lane);
+  };
+  auto load_x = [&](long nid, unsigned& msk, double& x0, double& x1, double& x2) {
+    msk = 0; x0 = x1 = x2 = 0.0;
+    if (nid < 0) return;
+    if (MODE == LVEC) {
+      if (ESS) msk = io.essmask[nid];
+      x0 = x[nid]; x1 = x[io.nnodes + nid]; x2 = x[2 * io.nnodes + nid];
+    } else {
+      x0 = x[nid]; x1 = x[nid + 8]; x2 = x[nid + 16];
+    }
+  };
+
+  long nid_c = load_nid(wt0), nid_n = load_nid(wt0 + stride);
+  unsigned msk_c; double xc0, xc1, xc2;
+  load_x(nid_c, msk_c, xc0, xc1, xc2);
+
+  int s = 0;
+  uint32_t phase = 0;
+  for (long wt = wt0; wt < nwt; wt += stride) {
+    // prefetch: connectivity two tiles ahead, nodal values one tile ahead
+    const long nid_n2 = load_nid(wt + 2 * stride);
+    unsigned msk_n; double xn0, xn1, xn2;
+    load_x(nid_n, msk_n, xn0, xn1, xn2);
+
+    const double u0 = (msk_c & 1) ? 0.0 : xc0, u1 = (msk_c & 2) ? 0.0 : xc1, u2 = (msk_c & 4) ? 0.0 : xc2;
+    double d00, d01, d02, d10, d11, d12, d20, d21, d22;
+    nodal_to_qp_grad(u0, lane, d00, d01, d02);
+    nodal_to_qp_grad(u1, lane, d10, d11, d12);
+    nodal_to_qp_grad(u2, lane, d20, d21, d22);
+
+    mbar_wait(&full[s], phase);
+
+    const bool active = nid_c >= 0;
+    double t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0, t20 = 0, t21 = 0, t22 = 0;
+    if (active) {
+      const unsigned char* sc = ring + s * kWarpStageBytes;
+      const double* Jq = reinterpret_cast<const double*>(sc + 4 * kCElemSmem + el * kJElemBytes) + lane * 9;
+      double J[9], adj[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+      const double det = adjugate(J, adj);
+      const double c = dt * kWq / det;
+      const double g00 = d00 * adj[0] + d01 * adj[3] + d02 * adj[6];
+      const double g01 = d00 * adj[1] + d01 * adj[4] + d02 * adj[7];
+      const double g02 = d00 * adj[2] + d01 * adj[5] + d02 * adj[8];
+      const double g10 = d10 * adj[0] + d11 * adj[3] + d12 * adj[6];
+      const double g11 = d10 * adj[1] + d11 * adj[4] + d12 * adj[7];
+      const double g12 = d10 * adj[2] + d11 * adj[5] + d12 * adj[8];
+      const double g20 = d20 * adj[0] + d21 * adj[3] + d22 * adj[6];
+      const double g21 = d20 * adj[1] + d21 * adj[4] + d22 * adj[7];
+      const double g22 = d20 * adj[2] + d21 * adj[5] + d22 * adj[8];
+      const double eps[6] = {c * g00, c * g11, c * g22, c * (g12 + g21), c * (g02 + g20), c * (g01 + g10)};
+      const double2* C2 = reinterpret_cast<const double2*>(sc + el * kCElemSmem + (lane >> 2) * (kCHalfBytes + 16) + (lane & 3) * 288);
+      double S[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int Jc = 0; Jc < 6; ++Jc) {
+        const double2 a = C2[Jc * 3 + 0], b = C2[Jc * 3 + 1], cc = C2[Jc * 3 + 2];
+        S[0] += a.x * eps[Jc]; S[1] += a.y * eps[Jc];
+        S[2] += b.x * eps[Jc]; S[3] += b.y * eps[Jc];
+        S[4] += cc.x * eps[Jc]; S[5] += cc.y * eps[Jc];
+      }
+      t00 = adj[0] * S[0] + adj[1] * S[5] + adj[2] * S[4];
+      t01 = adj[0] * S[5] + adj[1] * S[1] + adj[2] * S[3];
+      t02 = adj[0] * S[4] + adj[1] * S[3] + adj[2] * S[2];
+      t10 = adj[3] * S[0] + adj[4] * S[5] + adj[5] * S[4];
+      t11 = adj[3] * S[5] + adj[4] * S[1] + adj[5] * S[3];
+      t12 = adj[3] * S[4] + adj[4] * S[3] + adj[5] * S[2];
+      t20 = adj[6] * S[0] + adj[7] * S[5] + adj[8] * S[4];
+      t21 = adj[6] * S[5] + adj[7] * S[1] + adj[8] * S[3];
+      t22 = adj[6] * S[4] + adj[7] * S[3] + adj[8] * S[2];
+    }
+    // this stage's shared memory is dead: refill it before the output butterflies
+    __syncwarp();
+    {
+      const long tnext = wt + (long)STAGES * stride;
+      if (tnext < nwt) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(tnext, s);
+      }
+    }
+    const double y0 = qp_grad_to_nodal(t00, t10, t20, lane);
+    const double y1 = qp_grad_to_nodal(t01, t11, t21, lane);
+    const double y2 = qp_grad_to_nodal(t02, t12, t22, lane);
+    if (active) {
+      if (MODE == LVEC) {
+        if (!(msk_c & 1)) red_add_f64(&y[nid_c], y0);
+        if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
+        if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], y2);
+      } else {
+        y[nid_c] += y0; y[nid_c + 8] += y1; y[nid_c + 16] += y2;
+      }
+    }
+    nid_c = nid_n; nid_n = nid_n2;
+    msk_c = msk_n; xc0 = xn0; xc1 = xn1; xc2 = xn2;
+    if (++s == STAGES) { s = 0; phase ^= 1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Residual action: y_{a,k} += sum_q W_q [adj(J) sigma](j,k) G(a,j,q)
 // Replaces ExaNLFIntegrator::AssemblePA (three passes, src/mechanics_integrators.cpp:160-314)
 // + AddMultPA (:518-557) [+ restriction^T and essential-dof zeroing of MultVec,

@@ -140,6 +140,12 @@ inline std::string build_material(MatDev& m, int xtal, int kin, const double* p,
   if (xtal == XTAL_FCC) slip_fcc(m);
   else if (xtal == XTAL_BCC) slip_bcc(m);
   else slip_hcp(m, cOverA);
+  if (kin != KIN_KMBALD) {
+    m.pl_t_min = std::pow(1.0e-60, m.xm);
+    m.pl_t_max = std::pow(1.0e45, m.xm);
+    m.pl_max = std::exp((1.0 / m.xm - 1.0) * std::log(m.pl_t_max));
+  }
+  m.ln_ovf = std::log(1.0e45);
   m.gruneisen = p[i++];
   const double ec0 = p[i++];
   m.dtde = 1.0 / cvav;

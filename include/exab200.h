@@ -132,7 +132,8 @@ int exab200_grad_calc(exab200_ctx* ctx, const double* d_jac, const double* d_fie
 long exab200_launch_count(const exab200_ctx* ctx);
 
 /* Tuning knobs for the PA gradient apply: persistent CTAs per SM (default 1) and tile variant
- * (0: 16 elems x 4 stages, 1: 16x2, 2: 32x2, 3: 8x4, 4: 16x3) -- benchmarking only. */
+ * (CTA-tile kernel 0: 16 elems x 4 stages, 1: 16x2, 2: 32x2, 3: 8x4, 4: 16x3; warp-private pipelines
+ * 10: 4 warps x 2 stages (default), 11: 4x3, 12: 8x2, 13: 2x3, 14: 4x4, 15: 3x3) -- benchmarking only. */
 int exab200_set_tuning(exab200_ctx* ctx, int ctas_per_sm, int variant);
 
 #ifdef __cplusplus

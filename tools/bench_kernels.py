@@ -70,15 +70,15 @@ def main():
     ctx.grad_setup(dt, mg, jac)
     x = torch.randn(3 * nn, **f64)
     y = torch.empty_like(x)
-    cfgs = [(1, 0)]
+    cfgs = [(2, 10)]
     if sweep:
-        cfgs = [(1, 0), (2, 1), (1, 2), (4, 3), (3, 3), (1, 4), (2, 0)]
+        cfgs = [(2, 1), (2, 10), (1, 11), (1, 12), (3, 13), (1, 14), (2, 15), (4, 13), (1, 10), (3, 10)]
     for ctas, var in cfgs:
         ctx.set_tuning(ctas, var)
         t_med, t_min = timeit(lambda: ctx.grad_mult(x, y), iters=20, warm=3)
         gbs = ne * 3264 / t_med / 1e6
         res["grad_mult_v%d_c%d" % (var, ctas)] = dict(ms=t_med, ms_min=t_min, GBps=gbs, frac=gbs / peak)
-    ctx.set_tuning(1, 0)
+    ctx.set_tuning(2, 10)
     r = torch.empty_like(x)
     t_med, _ = timeit(lambda: ctx.residual(jac, s1, r))
     res["residual"] = dict(ms=t_med, GBps=ne * 1152 / t_med / 1e6)
