@@ -23,7 +23,7 @@ SYMBOLS = [
     "exab200_num_state_vars", "exab200_set_essential_mask", "exab200_hist_init",
     "exab200_setup_jacobians", "exab200_model_setup", "exab200_model_setup_evec",
     "exab200_failed_points", "exab200_residual_evec", "exab200_residual", "exab200_grad_setup",
-    "exab200_grad_mult_evec", "exab200_grad_mult", "exab200_grad_diag_evec", "exab200_grad_diag",
+    "exab200_grad_mult_evec", "exab200_grad_mult", "exab200_grad_mult_ex", "exab200_grad_diag_evec", "exab200_grad_diag",
     "exab200_ea_assemble", "exab200_ea_mult_evec", "exab200_vol_sum", "exab200_calc_dp",
     "exab200_grad_calc", "exab200_launch_count", "exab200_set_tuning",
 ]
@@ -151,6 +151,9 @@ class Context:
 
     def grad_mult(self, xL, yL, local_action=False):
         _chk(lib().exab200_grad_mult(self._h, _ptr(xL), _ptr(yL), int(local_action), _stream()))
+
+    def grad_mult_ex(self, xL, yL, flags=0, dot_accum=None):
+        _chk(lib().exab200_grad_mult_ex(self._h, _ptr(xL), _ptr(yL), int(flags), _ptr(dot_accum), _stream()))
 
     def grad_diag_evec(self, dE):
         _chk(lib().exab200_grad_diag_evec(self._h, _ptr(dE), _stream()))

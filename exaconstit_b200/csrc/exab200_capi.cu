@@ -77,7 +77,7 @@ static int launch_gm(exab200_ctx* c, const double* x, double* y, ElemIO io, cuda
   return 0;
 }
 template <int NW, int STAGES, int MODE, bool ESS>
-static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
+static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
   constexpr int smem = NW * STAGES * kWarpStageBytes + NW * STAGES * 8;
   static bool attr_set = false;
   if (!attr_set) {
@@ -88,12 +88,13 @@ static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cud
   long grid = (long)c->sm_count * c->ctas_per_sm;
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
   k_grad_mult_pa_w<NW, STAGES, MODE, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->d_matgrad, c->d_jac, x, y, io,
-                                                                                  c->cfg.nelems, c->grad_dt);
+                                                                                  c->cfg.nelems, c->grad_dt, dot);
   POST_LAUNCH(c);
   return 0;
 }
 template <int MODE, bool ESS>
-static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
+static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot = nullptr) {
+  if (dot && c->variant < 10) return fail("fused dot product needs a warp-pipelined variant (>= 10)");
   switch (c->variant) {
     case 0: return launch_gm<16, 4, MODE, ESS>(c, x, y, io, st);
     case 1: return launch_gm<16, 2, MODE, ESS>(c, x, y, io, st);
@@ -101,13 +102,13 @@ static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemI
     case 3: return launch_gm<8, 4, MODE, ESS>(c, x, y, io, st);
     case 4: return launch_gm<16, 3, MODE, ESS>(c, x, y, io, st);
     // warp-private pipelines {warps per CTA, stages}
-    case 10: return launch_gmw<4, 2, MODE, ESS>(c, x, y, io, st);
-    case 11: return launch_gmw<4, 3, MODE, ESS>(c, x, y, io, st);
-    case 12: return launch_gmw<8, 2, MODE, ESS>(c, x, y, io, st);
-    case 13: return launch_gmw<2, 3, MODE, ESS>(c, x, y, io, st);
-    case 14: return launch_gmw<4, 4, MODE, ESS>(c, x, y, io, st);
-    case 15: return launch_gmw<3, 3, MODE, ESS>(c, x, y, io, st);
-    default: return launch_gmw<4, 2, MODE, ESS>(c, x, y, io, st);
+    case 10: return launch_gmw<4, 2, MODE, ESS>(c, x, y, io, st, dot);
+    case 11: return launch_gmw<4, 3, MODE, ESS>(c, x, y, io, st, dot);
+    case 12: return launch_gmw<8, 2, MODE, ESS>(c, x, y, io, st, dot);
+    case 13: return launch_gmw<2, 3, MODE, ESS>(c, x, y, io, st, dot);
+    case 14: return launch_gmw<4, 4, MODE, ESS>(c, x, y, io, st, dot);
+    case 15: return launch_gmw<3, 3, MODE, ESS>(c, x, y, io, st, dot);
+    default: return launch_gmw<4, 2, MODE, ESS>(c, x, y, io, st, dot);
   }
 }
 
@@ -341,26 +342,31 @@ int exab200_grad_mult_evec(exab200_ctx* c, const double* d_x_E, double* d_y_E, v
   return launch_grad_mult_pa<EVEC, false>(c, d_x_E, d_y_E, io, (cudaStream_t)stream);
 }
 
-int exab200_grad_mult(exab200_ctx* c, const double* d_x_L, double* d_y_L, int local_action, void* stream) {
+int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int flags, double* d_dot_accum, void* stream) {
   NEED_L(c);
   if (!c->d_matgrad) return fail("grad_setup has not been called");
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(d_y_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
+  const bool local_action = flags & EXAB200_LOCAL_ACTION;
+  if (!(flags & EXAB200_NO_ZERO)) CK(cudaMemsetAsync(d_y_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
   const bool ess = c->have_ess && !local_action;
   ElemIO io{c->d_e2n, ess ? c->d_ess : nullptr, c->cfg.nnodes};
   if (c->cfg.assembly == EXAB200_EA) {
-    k_ea_mult<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_x_L, d_y_L, io, c->cfg.nelems);
+    k_ea_mult<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_x_L, d_y_L, io, c->cfg.nelems, d_dot_accum);
     POST_LAUNCH(c);
     return 0;
   }
-  if (ess) return launch_grad_mult_pa<LVEC, true>(c, d_x_L, d_y_L, io, st);
-  return launch_grad_mult_pa<LVEC, false>(c, d_x_L, d_y_L, io, st);
+  if (ess) return launch_grad_mult_pa<LVEC, true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+  return launch_grad_mult_pa<LVEC, false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+}
+
+int exab200_grad_mult(exab200_ctx* c, const double* d_x_L, double* d_y_L, int local_action, void* stream) {
+  return exab200_grad_mult_ex(c, d_x_L, d_y_L, local_action ? EXAB200_LOCAL_ACTION : 0, nullptr, stream);
 }
 
 int exab200_ea_mult_evec(exab200_ctx* c, const double* d_emat, const double* d_x_E, double* d_y_E, void* stream) {
   if (!c) return fail("null ctx");
   ElemIO io{nullptr, nullptr, 0};
-  k_ea_mult<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_emat, d_x_E, d_y_E, io, c->cfg.nelems);
+  k_ea_mult<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_emat, d_x_E, d_y_E, io, c->cfg.nelems, nullptr);
   POST_LAUNCH(c);
   return 0;
 }

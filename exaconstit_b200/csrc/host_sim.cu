@@ -144,6 +144,47 @@ __global__ void k_xpby(double* __restrict__ d, const double* __restrict__ z, dou
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = z[i] + beta * d[i];
 }
+// CG step 1 (device-resident scalars): alpha = nom/den; x += alpha d; r -= alpha z;
+// partial[blk] = sum over uniquely-owned dofs of r . (M r), M = diag(dinv) or identity
+__global__ void __launch_bounds__(256) k_cg_step1(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
+                                                  const double* __restrict__ z, const double* __restrict__ dinv,
+                                                  const double* __restrict__ nom, const double* __restrict__ den, long nn,
+                                                  long n_owned, double* __restrict__ partial) {
+  const double alpha = *nom / *den;
+  double s = 0.0;
+  const long total = 3 * nn;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    x[i] += alpha * d[i];
+    const double rn = r[i] - alpha * z[i];
+    r[i] = rn;
+    const long c = i / nn, n = i - c * nn;
+    if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+  }
+  __shared__ double red[8];
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+// CG step 2: beta = betanom/nom; d = M r + beta d; y = 0 (output of the next operator apply)
+__global__ void __launch_bounds__(256) k_cg_step2(double* __restrict__ d, const double* __restrict__ r,
+                                                  const double* __restrict__ dinv, double* __restrict__ y,
+                                                  const double* __restrict__ betanom, const double* __restrict__ nom, long n) {
+  const double beta = *betanom / *nom;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double ri = r[i];
+    d[i] = (dinv ? dinv[i] * ri : ri) + beta * d[i];
+    y[i] = 0.0;
+  }
+}
+// nom = betanom; den = 0 (accumulator of the next fused x^T K x)
+__global__ void k_cg_roll(double* nom, double* den, const double* betanom) { *nom = *betanom; *den = 0.0; }
+
 // y = a x + b y
 __global__ void k_axpby(double* __restrict__ y, const double* __restrict__ x, double a, double b, long n) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,6 +229,7 @@ __global__ void k_plane_pack(const double* __restrict__ v, double* __restrict__ 
   buf[i] = v[c * nn + off + n];
 }
 static long g_host_launches = 0;
+static inline long& g_host_launches_ref() { return g_host_launches; }
 static inline unsigned nb(long n) { ++g_host_launches; return (unsigned)((n + 255) / 256); }
 
 // ---------------------------------------------------------------- per-kernel timing ---------
@@ -274,6 +316,15 @@ class SlabComm {
     HCK(cudaStreamSynchronize(stream));
     return h_scal[0];
   }
+  // partial sums -> one device scalar (+ allreduce), no host involvement
+  void ReduceToDevice(double* d_out) {
+    k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, d_out);
+    ++g_host_launches_ref();
+    if (nranks > 1) { NCK(g_nccl.AllReduce(d_out, d_out, 1, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+  }
+  void AllReduceDevice(double* d_buf, int n) {
+    if (nranks > 1) { NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+  }
   // sum-reduce a small device buffer in place and fetch it
   void AllReduceFetch(double* d_buf, int n, double* h_out) {
     if (nranks > 1) { NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
@@ -339,6 +390,8 @@ class GradientOperator : public Operator {
   explicit GradientOperator(const NonlinearMechOperator* o) : op(o) {}
   void Mult(const Vector& x, Vector& y) const override;       // TMult<false>
   void LocalMult(const Vector& x, Vector& y) const;           // TMult<true>
+  // y += K x into a pre-zeroed y and *d_den += x^T K x (fused CG denominator); halo-summed
+  void MultAccDot(const Vector& x, Vector& y, double* d_den) const;
   void AssembleDiagonal(Vector& diag) const;
 };
 
@@ -408,6 +461,13 @@ void GradientOperator::Mult(const Vector& x, Vector& y) const {
   op->comm->HaloSum(y.Write());
   ++op->grad_mults;
 }
+void GradientOperator::MultAccDot(const Vector& x, Vector& y, double* d_den) const {
+  op->tm_grad_mult.Begin(op->stream);
+  XCK(exab200_grad_mult_ex(op->ctx, x.Read(), y.Write(), EXAB200_NO_ZERO, d_den, op->stream));
+  op->tm_grad_mult.End(op->stream);
+  op->comm->HaloSum(y.Write());
+  ++op->grad_mults;
+}
 void GradientOperator::LocalMult(const Vector& x, Vector& y) const {
   XCK(exab200_grad_mult(op->ctx, x.Read(), y.Write(), 1, op->stream));
   op->comm->HaloSum(y.Write());
@@ -452,40 +512,74 @@ class CGSolver {
   int max_iter = 1000;
   const Operator* oper = nullptr;
   const MechOperatorJacobiSmoother* prec = nullptr;
-  mutable Vector r, d, z;
+  mutable Vector r, d, z, scal;
   mutable int final_iter = 0, converged = 0;
   mutable long total_iters = 0;
-  CGSolver(SlabComm* c, cudaStream_t s, long n) : comm(c), stream(s), r(n), d(n), z(n) {}
+  double* h_bet = nullptr;  // pinned ring for the stopping test
+  cudaEvent_t ev[8];
+  CGSolver(SlabComm* c, cudaStream_t s, long n) : comm(c), stream(s), r(n), d(n), z(n), scal(8) {
+    HCK(cudaMallocHost(&h_bet, 8 * sizeof(double)));
+    for (int i = 0; i < 8; ++i) HCK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  }
+  ~CGSolver() {
+    if (h_bet) cudaFreeHost(h_bet);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ev[i]);
+  }
   void SetOperator(const Operator& op) { oper = &op; }
+  // Device-resident formulation of mfem::CGSolver::Mult (iterative_mode = false): the scalars nom, den,
+  // betanom live on the device; alpha/beta are formed inside the vector kernels; the denominator d^T A d is
+  // accumulated by the operator kernel itself.  The only host wait per iteration is on betanom (for the
+  // reference's stopping test), and it is placed AFTER the next direction update + operator apply have been
+  // enqueued -- those touch neither x nor r, so a positive test simply discards them -- which hides the
+  // host round trip behind the operator kernel.  Iteration-for-iteration identical to the reference loop.
   void Mult(const Vector& b, Vector& x) const {
     const long n = b.Size();
+    const long nn = n / 3;
+    const GradientOperator* A = static_cast<const GradientOperator*>(oper);
+    const double* dinv = prec->refresh ? prec->dinv.Read() : nullptr;  // identity smoother otherwise
+    double* d_nom = scal.d + 0; double* d_den = scal.d + 1; double* d_bet = scal.d + 2;
     HCK(cudaMemcpyAsync(r.d, b.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
     HCK(cudaMemsetAsync(x.d, 0, sizeof(double) * n, stream));
-    prec->Mult(r, z);
-    HCK(cudaMemcpyAsync(d.d, z.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+    if (dinv) prec->Mult(r, d);
+    else HCK(cudaMemcpyAsync(d.d, r.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
     double nom = comm->Dot(d.d, r.d);
     const double r0 = std::max(nom * rel_tol * rel_tol, abs_tol * abs_tol);
     converged = 0;
     final_iter = 0;
     if (nom <= r0) { converged = 1; return; }
-    oper->Mult(d, z);
-    double den = comm->Dot(z.d, d.d);
-    if (den <= 0.0 && den == 0.0) return;
+    double init[3] = {nom, 0.0, 0.0};
+    HCK(cudaMemcpyAsync(scal.d, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    HCK(cudaMemsetAsync(z.d, 0, sizeof(double) * n, stream));
+    A->MultAccDot(d, z, d_den);
+    comm->AllReduceDevice(d_den, 1);
+    {
+      double den;
+      HCK(cudaMemcpyAsync(&den, d_den, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      HCK(cudaStreamSynchronize(stream));
+      if (den <= 0.0 && den == 0.0) return;
+    }
     int i = 1;
     final_iter = max_iter;
     for (;;) {
-      const double alpha = nom / den;
-      k_cg_update<<<nb(n), 256, 0, stream>>>(x.d, r.d, d.d, z.d, alpha, n);
-      prec->Mult(r, z);
-      const double betanom = comm->Dot(r.d, z.d);
+      k_cg_step1<<<kRedBlocks, 256, 0, stream>>>(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, nn, comm->n_owned, comm->partial.d);
+      ++g_host_launches;
+      comm->ReduceToDevice(d_bet);
+      const int slot = i & 7;
+      HCK(cudaMemcpyAsync(h_bet + slot, d_bet, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      HCK(cudaEventRecord(ev[slot], stream));
+      const bool last = (i + 1 > max_iter);
+      if (!last) {
+        // speculative: next direction and operator apply (do not touch x, r)
+        k_cg_step2<<<nb(n), 256, 0, stream>>>(d.d, r.d, dinv, z.d, d_bet, d_nom, n);
+        k_cg_roll<<<1, 1, 0, stream>>>(d_nom, d_den, d_bet);
+        ++g_host_launches;
+        A->MultAccDot(d, z, d_den);
+        comm->AllReduceDevice(d_den, 1);
+      }
+      HCK(cudaEventSynchronize(ev[slot]));
+      const double betanom = h_bet[slot];
       if (betanom <= r0) { converged = 1; final_iter = i; break; }
       if (++i > max_iter) break;
-      const double beta = betanom / nom;
-      k_xpby<<<nb(n), 256, 0, stream>>>(d.d, z.d, beta, n);
-      oper->Mult(d, z);
-      den = comm->Dot(d.d, z.d);
-      if (den <= 0.0 && den == 0.0) { final_iter = i; break; }
-      nom = betanom;
     }
     total_iters += std::min(i, max_iter);
   }

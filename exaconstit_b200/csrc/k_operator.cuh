@@ -203,7 +203,8 @@ template <int NW, int STAGES, int MODE, bool ESS>
 __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __restrict__ matgrad,
                                                             const double* __restrict__ jac,
                                                             const double* __restrict__ x, double* __restrict__ y,
-                                                            ElemIO io, long nelems, double dt) {
+                                                            ElemIO io, long nelems, double dt,
+                                                            double* __restrict__ dot_accum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
   const int lane = l32 & 7;  // node / quadrature point
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
 
   int s = 0;
   uint32_t phase = 0;
+  double xdoty = 0.0;  // sum over this lane's (node, element) pairs of x . (K_e x_e): assembles to x^T K x
   for (long wt = wt0; wt < nwt; wt += stride) {
     // prefetch: connectivity two tiles ahead, nodal values one tile ahead
     const long nid_n2 = load_nid(wt + 2 * stride);
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
     const double y1 = qp_grad_to_nodal(t01, t11, t21, lane);
     const double y2 = qp_grad_to_nodal(t02, t12, t22, lane);
     if (active) {
+      xdoty += u0 * y0 + u1 * y1 + u2 * y2;
       if (MODE == LVEC) {
         if (!(msk_c & 1)) red_add_f64(&y[nid_c], y0);
         if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
@@ -340,6 +343,11 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
     nid_c = nid_n; nid_n = nid_n2;
     msk_c = msk_n; xc0 = xn0; xc1 = xn1; xc2 = xn2;
     if (++s == STAGES) { s = 0; phase ^= 1; }
+  }
+  if (dot_accum) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) xdoty += __shfl_xor_sync(kFull, xdoty, m);
+    if (l32 == 0) red_add_f64(dot_accum, xdoty);
   }
 }
 
@@ -672,7 +680,8 @@ __global__ void __launch_bounds__(128) k_assemble_ea(const double* __restrict__ 
 // ------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, const double* __restrict__ x,
-                                                 double* __restrict__ y, ElemIO io, long nelems) {
+                                                 double* __restrict__ y, ElemIO io, long nelems,
+                                                 double* __restrict__ dot_accum) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 7;
   const long e = gt >> 3;
@@ -702,8 +711,8 @@ __global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, 
     xe[a + 8] = __shfl_sync(kFull, u1, src);
     xe[a + 16] = __shfl_sync(kFull, u2, src);
   }
-  if (!active) return;
-  double r[3];
+  double r[3] = {0.0, 0.0, 0.0};
+  if (active) {
 #pragma unroll
   for (int cmp = 0; cmp < 3; ++cmp) {
     const double2* col = reinterpret_cast<const double2*>(ea + e * 576 + (long)(an + 8 * cmp) * 24);
@@ -722,6 +731,13 @@ __global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, 
     if (!(msk & 4)) red_add_f64(&y[2 * io.nnodes + nid], r[2]);
   } else {
     y[nid] += r[0]; y[nid + 8] += r[1]; y[nid + 16] += r[2];
+  }
+  }
+  if (dot_accum) {
+    double v = u0 * r[0] + u1 * r[1] + u2 * r[2];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) red_add_f64(dot_accum, v);
   }
 }
 

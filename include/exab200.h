@@ -104,6 +104,13 @@ int exab200_grad_setup(exab200_ctx* ctx, double dt, const double* d_matgrad, con
  * essential dofs of x are treated as zero and y[ess] = 0. */
 int exab200_grad_mult_evec(exab200_ctx* ctx, const double* d_x_E, double* d_y_E, void* stream);
 int exab200_grad_mult(exab200_ctx* ctx, const double* d_x_L, double* d_y_L, int local_action, void* stream);
+/* Same operator for a device-resident CG loop (the role mfem::CGSolver's oper->Mult + Dot(d, z) pair plays,
+ * src/system_driver.cpp:166-178): flags = EXAB200_LOCAL_ACTION | EXAB200_NO_ZERO (y_L is accumulated into; the
+ * caller zeroed it); if d_dot_accum != NULL, x^T K x (essential dofs of x as zero) is ADDED to *d_dot_accum
+ * from the element contributions, so the CG denominator costs no extra pass over the vectors. */
+enum { EXAB200_LOCAL_ACTION = 1, EXAB200_NO_ZERO = 2 };
+int exab200_grad_mult_ex(exab200_ctx* ctx, const double* d_x_L, double* d_y_L, int flags, double* d_dot_accum,
+                         void* stream);
 
 /* AssembleGradDiagonalPA / EA AssembleDiagonal (src/mechanics_integrators.cpp:625-748,1607-1805;
  * src/mechanics_operator_ext.cpp:95-123,228-265).  L form: diag[ess] = 1. */
