@@ -44,7 +44,8 @@ struct exab200_ctx {
   double* d_ea = nullptr;  // EA element matrices (assembly == EA)
   long launches = 0;
   int ctas_per_sm = 2;
-  int variant = 10;  // PA gradient-apply tile configuration, see kVariants
+  int variant = 10;
+  int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
 static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((nelems * 8 + threads - 1) / threads); }
@@ -148,6 +149,47 @@ __global__ void __launch_bounds__(256) k_grad_calc(const double* __restrict__ ja
 }
 
 
+template <int NSLIP, int MODE, int MINB>
+static int launch_k1(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0, const double* h0,
+                     double* s1, double* h1, double* mg, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_model_setup<NSLIP, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
+    attr_set = true;
+  }
+  const unsigned nb = eblocks(c->cfg.nelems, kJS);
+  k_model_setup<NSLIP, MODE, MINB><<<nb, kJS, kK1SmemBytes, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel,
+                                                                    MODE == LVEC ? c->d_e2n : nullptr, c->cfg.nnodes, s0, h0, s1,
+                                                                    h1, mg, c->cfg.nelems, 1, c->d_fail);
+  POST_LAUNCH(c);
+  return 0;
+}
+template <int NSLIP, int MODE>
+static int launch_k1_occ(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0,
+                         const double* h0, double* s1, double* h1, double* mg, cudaStream_t st) {
+  switch (c->k1_min_blocks) {
+    case 2: return launch_k1<NSLIP, MODE, 2>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+    case 4: return launch_k1<NSLIP, MODE, 4>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+    default: return launch_k1<NSLIP, MODE, 3>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+  }
+}
+
+// The reference skips the tangent transpose for EA on a device backend (src/mechanics_ecmech.cpp:155) and then
+// reads the row-major matrix as column-major; we always store d sigma_i/d eps_j at [j*6+i].
+static int model_setup_impl(exab200_ctx* c, int mode, double dt, const double* d_jac, const double* d_vel,
+                            const double* s0, const double* h0, double* s1, double* h1, double* mg, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!(dt > 0.0)) return fail("dt must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->mat.nslip == 12) {
+    if (mode == LVEC) return launch_k1_occ<12, LVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+    return launch_k1_occ<12, EVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+  }
+  if (mode == LVEC) return launch_k1_occ<24, LVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+  return launch_k1_occ<24, EVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+}
+
+
 extern "C" {
 
 const char* exab200_last_error(void) { return g_err.c_str(); }
@@ -206,9 +248,10 @@ void exab200_destroy(exab200_ctx* c) {
 int exab200_num_state_vars(const exab200_ctx* c) { return c ? c->mat.nhist : -1; }
 long exab200_launch_count(const exab200_ctx* c) { return c ? c->launches : -1; }
 int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
-  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8 || variant < 0 || variant > 15) return fail("bad tuning");
+  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8 || variant < 0 || (variant % 100) > 15 || variant > 415) return fail("bad tuning");
   c->ctas_per_sm = ctas_per_sm;
-  c->variant = variant;
+  c->variant = variant % 100;
+  if (variant >= 100) c->k1_min_blocks = variant / 100;  // e.g. 210 -> K1 with 2 blocks/SM, K2 variant 10
   return 0;
 }
 
@@ -239,31 +282,6 @@ int exab200_setup_jacobians(exab200_ctx* c, const double* d_xbeg, const double* 
   NEED_L(c);
   ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
   k_jacobians<<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_xbeg, d_vel, dt, d_jac, io, c->cfg.nelems);
-  POST_LAUNCH(c);
-  return 0;
-}
-
-static int model_setup_impl(exab200_ctx* c, int mode, double dt, const double* d_jac, const double* d_vel,
-                            const double* s0, const double* h0, double* s1, double* h1, double* mg, void* stream) {
-  if (!c) return fail("null ctx");
-  if (!(dt > 0.0)) return fail("dt must be positive");
-  // the reference skips the tangent transpose for EA on a device backend (src/mechanics_ecmech.cpp:155)
-  // and then reads the row-major matrix as column-major; we always store d sigma_i/d eps_j at [j*6+i].
-  const int transpose = 1;
-  cudaStream_t st = (cudaStream_t)stream;
-  const unsigned nb = eblocks(c->cfg.nelems, 128);
-  const long ne = c->cfg.nelems, nn = c->cfg.nnodes;
-  if (c->mat.nslip == 12) {
-    if (mode == LVEC)
-      k_model_setup<12, LVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
-    else
-      k_model_setup<12, EVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
-  } else {
-    if (mode == LVEC)
-      k_model_setup<24, LVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, c->d_e2n, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
-    else
-      k_model_setup<24, EVEC><<<nb, 128, 0, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel, nullptr, nn, s0, h0, s1, h1, mg, ne, transpose, c->d_fail);
-  }
   POST_LAUNCH(c);
   return 0;
 }

@@ -277,7 +277,7 @@ class SlabComm {
     n_owned = (rank == nranks - 1) ? nn : nn - plane;
     partial.SetSize(kRedBlocks);
     scal.SetSize(8);
-    HCK(cudaMallocHost(&h_scal, 8 * sizeof(double)));
+    HCK(cudaMallocHost(&h_scal, 64 * sizeof(double)));
     if (nranks > 1) {
       if (!g_nccl.load()) throw Abort{"NCCL library could not be loaded"};
       ncclUniqueId id;
@@ -661,7 +661,7 @@ struct exahost_sim {
   SlabComm comm;
   long nelems = 0, nnodes = 0, plane = 0;
   Vector stress0, stress1, matVars0, matVars1, matGrad;
-  Vector x_beg, v_sol, v_prev, ess_val, tmp, sums;
+  Vector x_beg, x_ref, v_sol, v_prev, ess_val, tmp, sums;
   std::vector<unsigned char> h_mask;
   std::unique_ptr<ExaCMechModel> model;
   std::unique_ptr<NonlinearMechOperator> oper;
@@ -763,6 +763,8 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
             xc[2 * s->nnodes + nd] = cfg->length[2] * (k + cfg->z0) / cfg->nz_total;
           }
       HCK(cudaMemcpy(s->x_beg.d, xc.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+      s->x_ref.SetSize(n);
+      HCK(cudaMemcpy(s->x_ref.d, xc.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     }
     // history: setStateVarData (src/mechanics_driver.cpp:1058-1154: state-file values + per-grain quaternion
     // at offset 9) followed by init_state_vars
@@ -900,6 +902,35 @@ int exahost_get(exahost_sim* s, int which, double* h_out) {
     HCK(cudaStreamSynchronize(s->stream));
     const Vector* v = which == 0 ? &s->stress0 : which == 1 ? &s->matVars0 : which == 2 ? &s->v_sol : &s->x_beg;
     HCK(cudaMemcpy(h_out, v->d, sizeof(double) * v->n, cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+
+// Additional volume averages of SystemDriver::UpdateModel (src/system_driver.cpp:470-553), evaluated on the state
+// just committed by exahost_step: out[0] = volume integral of the plastic work (not divided by the volume, as the
+// reference prints it), out[1..9] = volume-averaged deformation gradient F(i,t) at [1 + t*3 + i]
+// (CalculateDeformationGradient, src/mechanics_operator.cpp:393-427), out[10..15] = volume-averaged D^p in Voigt order.
+int exahost_extra_avgs(exahost_sim* s, double* out16) {
+  try {
+    HCK(cudaSetDevice(s->cfg.device));
+    const int nsv = exab200_num_state_vars(s->ctx);
+    const long npts = s->nelems * 8;
+    double h[48];
+    XCK(exab200_vol_sum(s->ctx, s->oper->el_jac.Read(), s->matVars0.Read(), nsv, s->sums.Write(), s->stream));
+    s->comm.AllReduceFetch(s->sums.d, nsv + 1, h);
+    out16[0] = h[2];
+    Vector jac_ref(s->nelems * 72), q9(npts * 9);
+    XCK(exab200_setup_jacobians(s->ctx, s->x_ref.Read(), nullptr, 0.0, jac_ref.Write(), s->stream));
+    XCK(exab200_grad_calc(s->ctx, jac_ref.Read(), s->x_beg.Read(), q9.Write(), s->stream));
+    XCK(exab200_vol_sum(s->ctx, s->oper->el_jac.Read(), q9.Read(), 9, s->sums.Write(), s->stream));
+    s->comm.AllReduceFetch(s->sums.d, 10, h);
+    for (int i = 0; i < 9; ++i) out16[1 + i] = h[i] / h[9];
+    XCK(exab200_calc_dp(s->ctx, s->matVars0.Read(), q9.Write(), s->stream));
+    XCK(exab200_vol_sum(s->ctx, s->oper->el_jac.Read(), q9.Read(), 9, s->sums.Write(), s->stream));
+    s->comm.AllReduceFetch(s->sums.d, 10, h);
+    const int pick[6] = {0, 4, 8, 5, 2, 1};
+    for (int i = 0; i < 6; ++i) out16[10 + i] = h[pick[i]] / h[9];
+    HCK(cudaStreamSynchronize(s->stream));
     return 0;
   } catch (const Abort& a) { g_err = a.msg; return 1; }
 }

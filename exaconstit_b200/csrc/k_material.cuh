@@ -51,6 +51,9 @@ constexpr double sqr2b3 = 0.816496580927726, sqr3b2 = 1.224744871391589;
 constexpr double idp_tiny_sqrt = 1.0e-90, idp_eps_sqrt = 1.0e-8;
 constexpr double gam_ratio_min = 1.0e-60, gam_ratio_ovf = 1.0e45;
 constexpr double e_scale = 5.0e-4, r_scale = 1.0e-2;
+// The 8x8 Jacobian of each thread lives in shared memory, entry k of thread t at smem[k * kJS + t]
+// (conflict-free, and off the local-memory / L2 path).
+constexpr int kJS = 128;
 
 __device__ __forceinline__ void svec_to_vecd(const double* s, double* v) {
   v[0] = sqr2i * (s[0] - s[1]);
@@ -144,12 +147,10 @@ __device__ __forceinline__ void exp_Jr(const double* xi, double Jm[3][3]) {
 }
 
 // ---- kinetics ---------------------------------------------------------------------------
-__device__ __forceinline__ void kin_power_law(const MatDev& m, double gam_w, double g, double tau, double& gdot,
-                                              double& dgdot_dtau) {
+__device__ __forceinline__ void kin_power_law(const MatDev& m, double gam_w, double g, double gi, double xmi, double tau,
+                                              double& gdot, double& dgdot_dtau) {
   gdot = 0.0;
   dgdot_dtau = 0.0;
-  const double xmi = 1.0 / m.xm;
-  const double gi = 1.0 / g;
   const double t = tau * gi, at = fabs(t);
   if (at <= m.pl_t_min) return;
   if (at > m.pl_t_max) {  // linear extrapolation beyond the overflow guard
@@ -241,23 +242,24 @@ __device__ __forceinline__ double kin_update_h(const MatDev& m, double h_n, doub
 }
 
 // ---- dense LU (n = 8) with partial pivoting on a local array ------------------------------
+#define JIDX(i, j) (((i) * 8 + (j)) * kJS)
 __device__ __noinline__ bool lu_factor8(double* A, int* piv) {
   for (int k = 0; k < 8; ++k) {
     int p = k;
-    double mx = fabs(A[k * 8 + k]);
+    double mx = fabs(A[JIDX(k, k)]);
     for (int i = k + 1; i < 8; ++i) {
-      const double v = fabs(A[i * 8 + k]);
+      const double v = fabs(A[JIDX(i, k)]);
       if (v > mx) { mx = v; p = i; }
     }
     if (mx == 0.0) return false;
     piv[k] = p;
     if (p != k)
-      for (int j = 0; j < 8; ++j) { const double t = A[k * 8 + j]; A[k * 8 + j] = A[p * 8 + j]; A[p * 8 + j] = t; }
-    const double inv = 1.0 / A[k * 8 + k];
+      for (int j = 0; j < 8; ++j) { const double t = A[JIDX(k, j)]; A[JIDX(k, j)] = A[JIDX(p, j)]; A[JIDX(p, j)] = t; }
+    const double inv = 1.0 / A[JIDX(k, k)];
     for (int i = k + 1; i < 8; ++i) {
-      const double f = A[i * 8 + k] * inv;
-      A[i * 8 + k] = f;
-      for (int j = k + 1; j < 8; ++j) A[i * 8 + j] -= f * A[k * 8 + j];
+      const double f = A[JIDX(i, k)] * inv;
+      A[JIDX(i, k)] = f;
+      for (int j = k + 1; j < 8; ++j) A[JIDX(i, j)] -= f * A[JIDX(k, j)];
     }
   }
   return true;
@@ -269,11 +271,11 @@ __device__ __noinline__ void lu_solve8(const double* A, const int* piv, double* 
     if (p != k) { const double t = b[k]; b[k] = b[p]; b[p] = t; }
   }
   for (int k = 0; k < 8; ++k)
-    for (int i = k + 1; i < 8; ++i) b[i] -= A[i * 8 + k] * b[k];
+    for (int i = k + 1; i < 8; ++i) b[i] -= A[JIDX(i, k)] * b[k];
   for (int i = 7; i >= 0; --i) {
     double s = b[i];
-    for (int j = i + 1; j < 8; ++j) s -= A[i * 8 + j] * b[j];
-    b[i] = s / A[i * 8 + i];
+    for (int j = i + 1; j < 8; ++j) s -= A[JIDX(i, j)] * b[j];
+    b[i] = s / A[JIDX(i, i)];
   }
 }
 
@@ -352,6 +354,7 @@ struct Problem {
     }
     shrate = 0.0;
     disRate = 0.0;
+    const double gi0 = 1.0 / g[0], xmi0 = (m.kin == KIN_KMBALD) ? 0.0 : 1.0 / m.xm;  // Voce: one resistance for all systems
 #pragma unroll 1
     for (int a = 0; a < NSLIP; ++a) {
       double tau = 0.0;
@@ -359,7 +362,7 @@ struct Problem {
       for (int i = 0; i < 5; ++i) tau += m.P[a][i] * T[i];
       double gd, dg;
       if (m.kin == KIN_KMBALD) kin_kmbald(m, gv(a), gam_w, gam_r, cev(a), tau, gd, dg);
-      else kin_power_law(m, gam_w, gv(a), tau, gd, dg);
+      else kin_power_law(m, gam_w, gv(a), gi0, xmi0, tau, gd, dg);
       gdot[a] = gd;
       shrate += fabs(gd);
       disRate += tau * gd;
@@ -406,14 +409,14 @@ struct Problem {
         double v = (i == j ? dt_ri : 0.0) + Mwp[i][j] + dDp[i][j];
 #pragma unroll
         for (int k = 0; k < 3; ++k) v += Me[i][k] * dWp[k][j];
-        Jac[i * 8 + j] = eps_si * v * e_scale;
+        Jac[JIDX(i, j)] = eps_si * v * e_scale;
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         double v = 0.0;
 #pragma unroll
         for (int l = 0; l < 3; ++l) v += Mdl[i][l] * JrM[l][k];
-        Jac[i * 8 + 5 + k] = -eps_si * v * r_scale;
+        Jac[JIDX(i, 5 + k)] = -eps_si * v * r_scale;
       }
     }
     const double Wl[3][3] = {{0.0, -w_lat[2], w_lat[1]}, {w_lat[2], 0.0, -w_lat[0]}, {-w_lat[1], w_lat[0], 0.0}};
@@ -425,14 +428,14 @@ struct Problem {
 #pragma unroll
         for (int i = 0; i < 5; ++i) t += 0.5 * Me[i][k] * dDp[i][j];
         t += -0.5 * (-0.5 * Me[j][k] * dt_ri + 0.5 * Medot[j][k]);
-        Jac[(5 + k) * 8 + j] = rot_si * dt * (dWp[k][j] + t) * e_scale;
+        Jac[JIDX(5 + k, j)] = rot_si * dt * (dWp[k][j] + t) * e_scale;
       }
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
         double v = (k == l ? dt_ri : 0.0);
 #pragma unroll
         for (int n = 0; n < 3; ++n) v -= Wl[k][n] * JrM[n][l];
-        Jac[(5 + k) * 8 + 5 + l] = rot_si * dt * v * r_scale;
+        Jac[JIDX(5 + k, 5 + l)] = rot_si * dt * v * r_scale;
       }
     }
   }
@@ -462,8 +465,8 @@ __device__ __noinline__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, do
     if (res <= tol) return nfev;
     double grad[8], Jg[8], nr[8];
     int piv[8];
-    for (int j = 0; j < 8; ++j) { double s = 0; for (int i = 0; i < 8; ++i) s += J[i * 8 + j] * R[i]; grad[j] = s; }
-    for (int i = 0; i < 8; ++i) { double s = 0; for (int j = 0; j < 8; ++j) s += J[i * 8 + j] * grad[j]; Jg[i] = s; }
+    for (int j = 0; j < 8; ++j) { double s = 0; for (int i = 0; i < 8; ++i) s += J[JIDX(i, j)] * R[i]; grad[j] = s; }
+    for (int i = 0; i < 8; ++i) { double s = 0; for (int j = 0; j < 8; ++j) s += J[JIDX(i, j)] * grad[j]; Jg[i] = s; }
     for (int i = 0; i < 8; ++i) nr[i] = -R[i];
     const bool have_newton = lu_factor8(J, piv);
     if (have_newton) lu_solve8(J, piv, nr);
@@ -497,22 +500,22 @@ __device__ __noinline__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, do
       double sn = 0.0;
       for (int i = 0; i < 8; ++i) { const double st = cb * nr[i] - ca * grad[i]; xt[i] = x[i] + st; sn += st * st; }
       sn = sqrt(sn);
-      prob.eval(m, xt, Rt, nullptr);
+      // Jacobian evaluated at the trial point straight into J (the factored old one is dead: a rejected
+      // step only needs grad, J grad and nr), so an accepted step needs no second evaluation
+      prob.eval(m, xt, Rt, J);
       ++nfev;
       const double rest = norm8(Rt);
       const bool finite = isfinite(rest);
       const double rho = (finite && pred > 0) ? (res - rest) / pred : -1.0;
       if (finite && rest < res) {
         accepted = true;
-        for (int i = 0; i < 8; ++i) x[i] = xt[i];
+        for (int i = 0; i < 8; ++i) { x[i] = xt[i]; R[i] = Rt[i]; }
         if (rho > xiLG && sn >= 0.99 * delta) delta = fmin(deltaMax, delta * xiIncDelta);
         else if (rho < xiLO) delta = fmax(deltaMin, fmax(delta, sn) * xiDecDelta * 2.0);
-        prob.eval(m, x, R, J);
-        ++nfev;
-        res = norm8(R);
+        res = rest;
       } else {
         delta = fmin(delta, sn) * xiDecDelta;
-        if (delta < deltaMin) { prob.eval(m, x, R, J); return -(nfev + 1); }
+        if (delta < deltaMin) { prob.eval(m, x, R, J); return -(nfev + 1); }  // restore state at x
       }
     }
   }
@@ -529,11 +532,10 @@ __device__ __noinline__ int solve_trdl(const MatDev& m, Problem<NSLIP>& prob, do
 // src/mechanics_ecmech.cpp:159-169; TRANSPOSE=false reproduces the EA-on-device quirk, :155).
 // fail_count is incremented for points whose local solve did not converge.
 // ------------------------------------------------------------------------------------------
-#ifndef EXAB_K1_MIN_BLOCKS
-#define EXAB_K1_MIN_BLOCKS 2
-#endif
-template <int NSLIP, int MODE>
-__global__ void __launch_bounds__(128, EXAB_K1_MIN_BLOCKS) k_model_setup(const MatDev* __restrict__ mp, double dt, double temp_k, const double* __restrict__ jac,
+constexpr int kJS = mat::kJS;
+constexpr int kK1SmemBytes = 64 * kJS * 8;  // 64 KB: one 8x8 Jacobian per thread
+template <int NSLIP, int MODE, int MINB>
+__global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restrict__ mp, double dt, double temp_k, const double* __restrict__ jac,
                                                      const double* __restrict__ vel, const int* __restrict__ e2n,
                                                      long nnodes, const double* __restrict__ stress0,
                                                      const double* __restrict__ hist0, double* __restrict__ stress1,
@@ -651,7 +653,9 @@ __global__ void __launch_bounds__(128, EXAB_K1_MIN_BLOCKS) k_model_setup(const M
     prob.eps_si = fmin(1.0 / eps_dot, 1.0e6 * dt);
     prob.rot_si = prob.dt_ri * prob.eps_si;
   }
-  double x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, R[8], J[64];
+  extern __shared__ double smJ[];
+  double* J = smJ + threadIdx.x;  // J(i,j) at J[JIDX(i,j)]
+  double x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, R[8];
   int nfev = solve_trdl<NSLIP>(m, prob, x, R, J, m.tol);
   if (nfev < 0) { atomicAdd(fail_count, 1); nfev = -nfev; }
   // ---- history out (StateVarsSetup copy + updates + kernel_postprocessing) ----

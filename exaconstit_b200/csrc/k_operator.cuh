@@ -241,35 +241,39 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
       if (t < nwt) issue(t, s);
   }
 
-  auto load_nid = [&](long wt) -> long {
+  // Connectivity is kept as the raw 32-bit value until it is used one iteration later, so that nothing
+  // (not even a sign extension) depends on the load in the iteration that issues it.
+  auto load_nid = [&](long wt) -> int {
     const long e = (wt << 2) + el;
     if (wt >= nwt || e >= nelems) return -1;
     if (MODE == LVEC) return io.e2n[e * 8 + lex_to_native(lane)];
-    return e * 24 + lex_to_native(lane);
+    return 0;  // EVEC: the offset is recomputed from the tile index
   };
-  auto load_x = [&](long nid, unsigned& msk, double& x0, double& x1, double& x2) {
+  auto evec_off = [&](long wt) -> long { return ((wt << 2) + el) * 24 + lex_to_native(lane); };
+  auto load_x = [&](int nid, long wt, unsigned& msk, double& x0, double& x1, double& x2) {
     msk = 0; x0 = x1 = x2 = 0.0;
     if (nid < 0) return;
     if (MODE == LVEC) {
       if (ESS) msk = io.essmask[nid];
       x0 = x[nid]; x1 = x[io.nnodes + nid]; x2 = x[2 * io.nnodes + nid];
     } else {
-      x0 = x[nid]; x1 = x[nid + 8]; x2 = x[nid + 16];
+      const long o = evec_off(wt);
+      x0 = x[o]; x1 = x[o + 8]; x2 = x[o + 16];
     }
   };
 
-  long nid_c = load_nid(wt0), nid_n = load_nid(wt0 + stride);
+  int nid_c = load_nid(wt0), nid_n = load_nid(wt0 + stride);
   unsigned msk_c; double xc0, xc1, xc2;
-  load_x(nid_c, msk_c, xc0, xc1, xc2);
+  load_x(nid_c, wt0, msk_c, xc0, xc1, xc2);
 
   int s = 0;
   uint32_t phase = 0;
   double xdoty = 0.0;  // sum over this lane's (node, element) pairs of x . (K_e x_e): assembles to x^T K x
   for (long wt = wt0; wt < nwt; wt += stride) {
     // prefetch: connectivity two tiles ahead, nodal values one tile ahead
-    const long nid_n2 = load_nid(wt + 2 * stride);
+    const int nid_n2 = load_nid(wt + 2 * stride);
     unsigned msk_n; double xn0, xn1, xn2;
-    load_x(nid_n, msk_n, xn0, xn1, xn2);
+    load_x(nid_n, wt + stride, msk_n, xn0, xn1, xn2);
 
     const double u0 = (msk_c & 1) ? 0.0 : xc0, u1 = (msk_c & 2) ? 0.0 : xc1, u2 = (msk_c & 4) ? 0.0 : xc2;
     double d00, d01, d02, d10, d11, d12, d20, d21, d22;
@@ -337,7 +341,8 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
         if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
         if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], y2);
       } else {
-        y[nid_c] += y0; y[nid_c + 8] += y1; y[nid_c + 16] += y2;
+        const long o = evec_off(wt);
+        y[o] += y0; y[o + 8] += y1; y[o + 16] += y2;
       }
     }
     nid_c = nid_n; nid_n = nid_n2;

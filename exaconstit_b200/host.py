@@ -123,6 +123,12 @@ class VoxelSim:
                     grad_mults=int(out[4]), seconds=float(out[5]), avg_stress=out[6:12].copy(),
                     dev_ms=float(out[12]), e2e_ms=float(out[13]))
 
+    def extra_avgs(self):
+        """additional_avgs of UpdateModel: plastic-work integral, <F> (9, [t*3+i]), <D^p> (6 Voigt)."""
+        out = np.zeros(16)
+        _chk(lib().exahost_extra_avgs(self._h, out.ctypes.data_as(C.c_void_p)))
+        return dict(pl_work=float(out[0]), def_grad=out[1:10].copy(), dp=out[10:16].copy())
+
     def get(self, which):
         sizes = {"stress": self.nelems * 48, "hist": self.nelems * 8 * self.nstatev, "vel": 3 * self.nnodes,
                  "xbeg": 3 * self.nnodes}
@@ -147,7 +153,7 @@ class VoxelSim:
     def set_tuning(self, ctas_per_sm, variant):
         _chk(lib().exahost_set_tuning(self._h, ctas_per_sm, variant))
 
-    def run(self, dts, bcs):
+    def run(self, dts, bcs, extras=False):
         """The reference's time loop (src/mechanics_driver.cpp:837-907). bcs: list of (step, ids, comps, vals)."""
         hist = []
         for ti, dt in enumerate(dts, start=1):
@@ -157,4 +163,6 @@ class VoxelSim:
                     self.set_bcs(b[1], b[2], b[3])
                     changed = True
             hist.append(self.step(float(dt), bc_changed=changed))
+            if extras:
+                hist[-1].update(self.extra_avgs())
         return hist

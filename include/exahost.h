@@ -47,6 +47,7 @@ int exahost_step(exahost_sim* sim, double dt, int bc_changed, const double* h_es
 int exahost_kernel_timing(exahost_sim* sim, int enable);
 int exahost_kernel_time(exahost_sim* sim, int which, double* total_ms, long* count, int reset);
 int exahost_set_tuning(exahost_sim* sim, int ctas_per_sm, int variant);
+int exahost_extra_avgs(exahost_sim* sim, double* out16);
 int exahost_get(exahost_sim* sim, int which, double* h_out);
 long exahost_counter(exahost_sim* sim, int which);
 void* exahost_stream(exahost_sim* sim);

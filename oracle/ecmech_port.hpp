@@ -661,7 +661,7 @@ struct UpdateProblem {
 // plays inside ExaCMech).  Returns the number of residual evaluations, <0 on failure.
 inline int solve_trdl(UpdateProblem& prob, double* x, double tol, int max_iter = 200) {
   const int n = 8;
-  double R[8], J[64], Rt[8], xt[8];
+  double R[8], J[64], Rt[8], Jt[64], xt[8];
   prob.eval(x, R, J);
   int nfev = 1;
   auto norm = [&](const double* v) { double s = 0; for (int i = 0; i < n; ++i) s += v[i] * v[i]; return std::sqrt(s); };
@@ -708,7 +708,7 @@ inline int solve_trdl(UpdateProblem& prob, double* x, double tol, int max_iter =
         pred = res - norm(lin);
       }
       for (int i = 0; i < n; ++i) xt[i] = x[i] + step[i];
-      prob.eval(xt, Rt, nullptr);
+      prob.eval(xt, Rt, Jt);  // Jacobian at the trial point: an accepted step needs no second evaluation
       ++nfev;
       const double rest = norm(Rt);
       const bool finite = std::isfinite(rest);
@@ -719,9 +719,9 @@ inline int solve_trdl(UpdateProblem& prob, double* x, double tol, int max_iter =
         std::memcpy(x, xt, sizeof(xt));
         if (rho > xiLG && norm(step) >= 0.99 * delta) delta = std::min(deltaMax, delta * xiIncDelta);
         else if (rho < xiLO) delta = std::max(deltaMin, std::max(delta, norm(step)) * xiDecDelta * 2.0);
-        prob.eval(x, R, J);
-        ++nfev;
-        res = norm(R);
+        std::memcpy(R, Rt, sizeof(Rt));
+        std::memcpy(J, Jt, sizeof(Jt));
+        res = rest;
       } else {
         delta = std::min(delta, norm(step)) * xiDecDelta;
         if (delta < deltaMin) return -nfev;

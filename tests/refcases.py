@@ -38,8 +38,21 @@ CASES = {
 }
 
 
+def cyclic_bcs(rate=0.001):
+    """test/data/voce_full_cyclic.toml:45-74: the z_max velocity flips sign at steps 11, 31, 51, 71."""
+    out = []
+    for step, sgn in zip([1, 11, 31, 51, 71], [1, -1, 1, -1, 1]):
+        out.append((step, [1, 2, 3, 4], [3, 1, 2, 3], [[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, sgn * rate]]))
+    return out
+
+
 def case_inputs(name):
     g = goldens()
+    if name == "voce_full_cyclic":
+        # Time.Fixed dt = 0.1, t_final = 7.0 (voce_full_cyclic.toml:100-103); FULL assembly run as PA here
+        return dict(n=(10, 10, 10), length=(1.0, 1.0, 1.0), xtal=0, kin=0, props=g["props_cp_voce"], temp_k=298.0,
+                    grain_ids=refined_grain_ids(), quats=g["voce_quats"], dts=np.full(70, 0.1), bcs=cyclic_bcs(),
+                    assembly=0, nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, 1000)), g["voce_full_cyclic_stress"]
     xtal, kin, pk, assembly, nr, kr, gk = CASES[name]
     return dict(n=(10, 10, 10), length=(1.0, 1.0, 1.0), xtal=xtal, kin=kin, props=g[pk], temp_k=298.0,
                 grain_ids=refined_grain_ids(), quats=g["voce_quats"], dts=g["custom_dt"], bcs=uniaxial_bcs(),

@@ -140,3 +140,33 @@ def test_grad_mult_properties_at_scale():
     ctx.grad_mult(ones, y0)
     assert (y0.abs().max() / scale).item() < 1e-12
     ctx.close()
+
+
+@pytest.mark.parametrize("assembly", [0, 1])
+def test_fused_cg_denominator(assembly):
+    """exab200_grad_mult_ex: y accumulates into a caller-zeroed vector and x^T K x (essential dofs of x as zero)
+    is added to the device accumulator from the element contributions."""
+    import torch
+    from exaconstit_b200 import capi
+    case = hc.make_case(n=5, seed=31, ngrains=4, assembly=assembly)
+    cpu = hc.run_oracle_hot_path(case)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    T = lambda a: torch.tensor(np.ascontiguousarray(a), **f64)
+    ne, nn, dt = case["ne"], case["nn"], case["dt"]
+    ctx = capi.Context(case["xtal"], case["kin"], case["props"], 298.0, ne, nn, case["e2n"], assembly, 0)
+    ctx.set_essential_mask(case["essmask"])
+    ctx.grad_setup(dt, T(cpu["matgrad"]), T(cpu["jac"]))
+    x = T(case["xvec"])
+    y = torch.zeros(3 * nn, **f64)
+    acc = torch.full((1,), 2.5, **f64)
+    ctx.grad_mult_ex(x, y, flags=2, dot_accum=acc)
+    torch.cuda.synchronize()
+    assert hc.rel_err(y.cpu().numpy(), cpu["y_grad"]) < OP_TOL
+    xm = case["xvec"].copy()
+    xm[hc.ess_dofs(case)] = 0.0
+    ref = float(xm @ cpu["y_grad"])
+    assert abs(acc.item() - 2.5 - ref) / abs(ref) < 1e-12
+    # second call accumulates on top (NO_ZERO) -- y doubles
+    ctx.grad_mult_ex(x, y, flags=2, dot_accum=None)
+    assert hc.rel_err(y.cpu().numpy(), 2.0 * cpu["y_grad"]) < OP_TOL
+    ctx.close()

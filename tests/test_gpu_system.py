@@ -64,3 +64,35 @@ def test_newton_line_search_variant():
     h, _, gold, _, _ = _gpu_run("voce_pa", 4, nl_solver=1)
     s = np.array([x["avg_stress"] for x in h])
     assert (np.abs(s - gold) / np.abs(gold[:, 2:3])).max() < 1.5e-5
+
+
+def test_additional_averages_match_goldens():
+    """voce_ea also pins plastic work, <F> and <D^p> (test/test_mechanics.py:114-117); 6 printed digits."""
+    from exaconstit_b200 import host
+    g = refcases.goldens()
+    inp, gold = refcases.case_inputs("voce_ea")
+    sim = host.VoxelSim(inp["n"], inp["length"], inp["xtal"], inp["kin"], inp["props"], inp["temp_k"],
+                        inp["grain_ids"], inp["quats"], assembly=1, nr=inp["nr"], kr=inp["kr"])
+    n = 8
+    hist = sim.run(inp["dts"][:n], inp["bcs"], extras=True)
+    sim.close()
+    plw = np.array([h["pl_work"] for h in hist])
+    F = np.array([h["def_grad"] for h in hist])
+    dp = np.array([h["dp"] for h in hist])
+    gp, gF, gd = g["voce_ea_pl_work"][:n], g["voce_ea_def_grad"][:n], g["voce_ea_dp_tensor"][:n]
+    assert np.abs(plw - gp).max() / np.abs(gp).max() < 2e-4
+    assert np.abs(F - gF).max() < 2e-6          # printed with 6 significant digits around 1.0
+    assert np.abs(dp - gd).max() / np.abs(gd).max() < 2e-4
+
+
+def test_cyclic_bc_reversal_matches_golden():
+    """voce_full_cyclic: the z_max velocity flips sign at step 11 (SolveInit corrector on BC-change steps)."""
+    from exaconstit_b200 import host
+    inp, gold = refcases.case_inputs("voce_full_cyclic")
+    sim = host.VoxelSim(inp["n"], inp["length"], inp["xtal"], inp["kin"], inp["props"], inp["temp_k"],
+                        inp["grain_ids"], inp["quats"], nr=inp["nr"], kr=inp["kr"])
+    n = 14
+    hist = sim.run(inp["dts"][:n], inp["bcs"])
+    sim.close()
+    s = np.array([h["avg_stress"] for h in hist])
+    assert np.abs(s[:, 2] - gold[:n, 2]).max() / np.abs(gold[:n, 2]).max() < 3e-5

@@ -51,3 +51,13 @@ def test_plastic_work_and_dp_goldens(orc):
     dp = r["extra"][:8, 1:7]
     gd = g["voce_ea_dp_tensor"][:8]
     assert np.abs(dp - gd).max() / np.abs(gd).max() < 2e-4
+
+
+def test_cyclic_reversal(orc):
+    """voce_full_cyclic_stress.txt across the first load reversal (BC change at step 11 -> SolveInit)."""
+    inp, gold = refcases.case_inputs("voce_full_cyclic")
+    inp["dts"] = inp["dts"][:14]
+    r = orc.sim_run(**inp)
+    assert r["rc"] == 0
+    err = np.abs(r["stress"][:, 2] - gold[:14, 2]).max() / np.abs(gold[:14, 2]).max()
+    assert err < 3e-5, err

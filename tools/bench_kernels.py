@@ -65,14 +65,17 @@ def main():
         hist0, h1 = h1, hist0
     print("failed points:", ctx.failed_points())
     res = {}
-    t_med, t_min = timeit(lambda: ctx.model_setup(dt, jac, vel, s0, hist0, s1, h1, mg), iters=5, warm=1)
-    res["model_setup"] = dict(ms=t_med, qpt_per_s=ne * 8 / t_med * 1e3, GBps=ne * 8 * 928 / t_med / 1e6)
+    for mb in ((2, 3, 4) if sweep else (3,)):
+        ctx.set_tuning(2, 100 * mb + 10)
+        t_med, t_min = timeit(lambda: ctx.model_setup(dt, jac, vel, s0, hist0, s1, h1, mg), iters=5, warm=1)
+        res["model_setup_minb%d" % mb] = dict(ms=t_med, qpt_per_s=ne * 8 / t_med * 1e3, GBps=ne * 8 * 928 / t_med / 1e6)
+    ctx.set_tuning(2, 210)
     ctx.grad_setup(dt, mg, jac)
     x = torch.randn(3 * nn, **f64)
     y = torch.empty_like(x)
     cfgs = [(2, 10)]
     if sweep:
-        cfgs = [(2, 1), (2, 10), (1, 11), (1, 12), (3, 13), (1, 14), (2, 15), (4, 13), (1, 10), (3, 10)]
+        cfgs = [(2, 10), (1, 12), (2, 15)]
     for ctas, var in cfgs:
         ctx.set_tuning(ctas, var)
         t_med, t_min = timeit(lambda: ctx.grad_mult(x, y), iters=20, warm=3)
