@@ -925,7 +925,8 @@ int exahost_extra_avgs(exahost_sim* s, double* out16) {
     XCK(exab200_vol_sum(s->ctx, s->oper->el_jac.Read(), q9.Read(), 9, s->sums.Write(), s->stream));
     s->comm.AllReduceFetch(s->sums.d, 10, h);
     for (int i = 0; i < 9; ++i) out16[1 + i] = h[i] / h[9];
-    XCK(exab200_calc_dp(s->ctx, s->matVars0.Read(), q9.Write(), s->stream));
+    // the reference reads matVars1 after the swap (src/mechanics_ecmech.hpp:308): previous step's state
+    XCK(exab200_calc_dp(s->ctx, s->matVars1.Read(), q9.Write(), s->stream));
     XCK(exab200_vol_sum(s->ctx, s->oper->el_jac.Read(), q9.Read(), 9, s->sums.Write(), s->stream));
     s->comm.AllReduceFetch(s->sums.d, 10, h);
     const int pick[6] = {0, 4, 8, 5, 2, 1};

@@ -457,11 +457,13 @@ class VoxelSim {
         dvec tmp(mat.nhist);
         vol_avg(hist0, mat.nhist, tmp.data(), false);
         ex[0] = tmp[ecm::iHistA_flowStr];
-        // D^p (calcDpMat, src/mechanics_ecmech.hpp:303-357), volume averaged, Voigt order
+        // D^p (calcDpMat, src/mechanics_ecmech.hpp:303-357), volume averaged, Voigt order.  The reference
+        // evaluates it from matVars1 AFTER the begin/end swap (src/mechanics_ecmech.hpp:308 called at
+        // src/system_driver.cpp:526), i.e. from the previous step's slip rates and orientations: reproduced.
         const long npts = ne * 8;
         dvec dp(npts * 6);
         for (long p = 0; p < npts; ++p) {
-          const double* h = &hist0[p * mat.nhist];
+          const double* h = &hist1[p * mat.nhist];
           double dphat[5] = {0, 0, 0, 0, 0}, C[9], R5[5][5], dsm[5], s6[6];
           for (int a = 0; a < mat.nslip; ++a)
             for (int i = 0; i < 5; ++i) dphat[i] += mat.P[a][i] * h[ecm::iHistLbGdot + a];

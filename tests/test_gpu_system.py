@@ -81,7 +81,7 @@ def test_additional_averages_match_goldens():
     dp = np.array([h["dp"] for h in hist])
     gp, gF, gd = g["voce_ea_pl_work"][:n], g["voce_ea_def_grad"][:n], g["voce_ea_dp_tensor"][:n]
     assert np.abs(plw - gp).max() / np.abs(gp).max() < 2e-4
-    assert np.abs(F - gF).max() < 2e-6          # printed with 6 significant digits around 1.0
+    assert np.abs(F - gF).max() < 6e-6          # goldens print 6 significant digits: +-5e-6 on values ~1
     assert np.abs(dp - gd).max() / np.abs(gd).max() < 2e-4
 
 
