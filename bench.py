@@ -115,6 +115,8 @@ def run_ours(args):
     sim = host.VoxelSim((n, n, n), (1.0, 1.0, 1.0), 0, 0, PROPS_VOCE, 298.0, grains, quats, assembly=0,
                         nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, args.krylov_iter), true_jacobi=args.true_jacobi,
                         rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
+    if nranks > 1 and not args.nccl_only:
+        sim.enable_peer_collectives(dist)
     mask, ess_val = sim.set_bcs(*BC)
     ess_pinned = np.ascontiguousarray(ess_val)
     vel_out = np.zeros(3 * sim.nnodes)
@@ -170,7 +172,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%d^3 voxel, %d Voronoi grains, FCC Voce, PA + PCG (identity smoother, %d-iter cap), "
                                    "uniaxial velocity BC" % (n, args.grains, args.krylov_iter),
-                       "mesh": [n, n, n], "partition": "z-slab x%d" % nranks, "true_jacobi": bool(args.true_jacobi),
+                       "mesh": [n, n, n], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi),
                        "cache": "inputs >> L2 (%.1f GB of quadrature data per rank)" % (ne_local * 8 * (36 + 9 + 2 * 28 + 12) * 8 / 1e9),
                        "newton_iters": newton, "pcg_iters": pcg, "model_setups": setups, "grad_mults": gmults},
             "e2e": {"value": newton / (e2e_ms * 1e-3), "unit": "Newton-steps/s",
@@ -315,6 +317,7 @@ def main():
     ap.add_argument("--krylov-iter", type=int, default=1000)
     ap.add_argument("--true-jacobi", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="use NCCL for the CG-loop exchanges instead of the peer-memory kernels")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     if args.impl == "reference":

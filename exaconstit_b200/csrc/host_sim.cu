@@ -261,6 +261,98 @@ struct KernelTimer {
   }
 };
 
+// ---------------------------------------------------------------- NVLink peer-memory collectives
+// Every rank owns a small "mailbox" in device memory that its peers map through CUDA IPC.  The two
+// latency-critical exchanges of the CG loop are done by single kernels that store straight into the
+// peers' mailboxes over NVLink and synchronise through release/acquire flags there:
+//   * interface-plane sum with the z-neighbours (k_halo_p2p)
+//   * all-reduce of up to 8 scalars over all ranks, summed in rank order => bitwise identical on every
+//     rank and run to run (k_allreduce_p2p)
+// Sequence numbers are monotonic and slots are double-buffered by parity, which is sufficient because a
+// rank can only be one collective ahead of a peer it exchanges with.
+// Mailbox layout (doubles): [0,64) flags as u64: 0 halo-from-lo, 1 halo-from-hi, 8+r scalar-from-rank-r,
+// 16 block counter, 17 error;  [64,192) scalar slots [par][rank][8];  [192, 192+12*plane) halo slots
+// [from-lo | from-hi][par][3*plane].
+constexpr int kMbFlags = 0, kMbScal = 64, kMbHalo = 192;
+constexpr long long kSpinLimit = 4000000000LL;  // ~2 s: turn a lost peer into an error instead of a hang
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq, double* mb) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < seq) {
+    if (clock64() - t0 > kSpinLimit) { reinterpret_cast<unsigned long long*>(mb)[17] = 1ull; return false; }
+  }
+  return true;
+}
+__device__ __forceinline__ double ld_cg(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// v: local L-vector; mb: my mailbox; lo/hi: peers' mailboxes (nullptr at the ends of the rank line)
+__global__ void __launch_bounds__(256) k_halo_p2p(double* __restrict__ v, double* mb, double* lo, double* hi, long nn,
+                                                  long plane, unsigned long long seq) {
+  const int par = (int)(seq & 1);
+  const long n3 = 3 * plane, top = nn - plane;
+  // push: my bottom plane -> lower neighbour's "from-hi" slot, my top plane -> upper neighbour's "from-lo" slot
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)gridDim.x * blockDim.x) {
+    const long c = i / plane, n = i - c * plane;
+    if (lo) lo[kMbHalo + (2 + par) * n3 + i] = v[c * nn + n];
+    if (hi) hi[kMbHalo + (0 + par) * n3 + i] = v[c * nn + top + n];
+  }
+  __threadfence_system();
+  __syncthreads();
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(mb);
+  if (threadIdx.x == 0) {
+    const unsigned long long prev = atomicAdd(&flags[16], 1ull);
+    if (prev == gridDim.x - 1) {
+      flags[16] = 0ull;
+      __threadfence_system();
+      if (lo) st_release_sys(reinterpret_cast<unsigned long long*>(lo) + 1, seq);  // I am the lower one's "hi"
+      if (hi) st_release_sys(reinterpret_cast<unsigned long long*>(hi) + 0, seq);  // I am the upper one's "lo"
+    }
+    if (lo) spin_until(&flags[0], seq, mb);
+    if (hi) spin_until(&flags[1], seq, mb);
+  }
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)gridDim.x * blockDim.x) {
+    const long c = i / plane, n = i - c * plane;
+    if (lo) v[c * nn + n] += ld_cg(&mb[kMbHalo + (0 + par) * n3 + i]);
+    if (hi) v[c * nn + top + n] += ld_cg(&mb[kMbHalo + (2 + par) * n3 + i]);
+  }
+}
+
+struct PeerTable { double* p[8]; };
+
+// in-place sum of val[0..n) over all ranks, n <= 8; one warp
+__global__ void k_allreduce_p2p(double* __restrict__ val, PeerTable peers, int rank, int nranks, int n,
+                                unsigned long long seq) {
+  const int lane = threadIdx.x;
+  const int par = (int)(seq & 1);
+  double* mb = peers.p[rank];
+  if (lane < nranks) {
+    double* dst = peers.p[lane] + kMbScal + (par * 8 + rank) * 8;
+    for (int k = 0; k < n; ++k) dst[k] = val[k];
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long*>(peers.p[lane]) + 8 + rank, seq);
+    spin_until(reinterpret_cast<unsigned long long*>(mb) + 8 + lane, seq, mb);
+  }
+  __syncwarp();
+  if (lane < n) {
+    double s = 0.0;
+    for (int r = 0; r < nranks; ++r) s += ld_cg(&mb[kMbScal + (par * 8 + r) * 8 + lane]);  // rank order: deterministic
+    val[lane] = s;
+  }
+}
+
 // ---------------------------------------------------------------- communicator --------------
 class SlabComm {
  public:
@@ -271,6 +363,12 @@ class SlabComm {
   Vector send_lo, send_hi, recv_lo, recv_hi, partial, scal;
   double* h_scal = nullptr;  // pinned
   long n_allreduce = 0, n_halo = 0;
+  // NVLink peer-memory path
+  Vector mailbox;
+  PeerTable peers{};
+  bool use_p2p = false;
+  unsigned long long seq_halo = 0, seq_scal = 0;
+  std::vector<void*> opened;
 
   void Init(int rank_, int nranks_, const void* nccl_id, cudaStream_t s, long nn_, long plane_) {
     rank = rank_; nranks = nranks_; stream = s; nn = nn_; plane = plane_;
@@ -284,9 +382,36 @@ class SlabComm {
       std::memcpy(&id, nccl_id, sizeof(id));
       NCK(g_nccl.CommInitRank(&comm, nranks, id, rank));
       send_lo.SetSize(3 * plane); send_hi.SetSize(3 * plane); recv_lo.SetSize(3 * plane); recv_hi.SetSize(3 * plane);
+      mailbox.SetSize(kMbHalo + 12 * plane);
+      HCK(cudaMemset(mailbox.d, 0, sizeof(double) * mailbox.n));
     }
   }
+  void GetHandle(void* out64) {
+    cudaIpcMemHandle_t h;
+    HCK(cudaIpcGetMemHandle(&h, mailbox.d));
+    static_assert(sizeof(h) == 64, "ipc handle size");
+    std::memcpy(out64, &h, 64);
+  }
+  void SetPeers(const void* handles) {
+    for (int r = 0; r < nranks; ++r) {
+      if (r == rank) { peers.p[r] = mailbox.d; continue; }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+      void* ptr = nullptr;
+      HCK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      opened.push_back(ptr);
+      peers.p[r] = static_cast<double*>(ptr);
+    }
+    use_p2p = true;
+  }
+  bool PeerError() {
+    if (!use_p2p) return false;
+    unsigned long long e = 0;
+    cudaMemcpy(&e, reinterpret_cast<unsigned long long*>(mailbox.d) + 17, 8, cudaMemcpyDeviceToHost);
+    return e != 0;
+  }
   ~SlabComm() {
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
   }
@@ -296,6 +421,15 @@ class SlabComm {
     if (nranks == 1) return;
     const bool lo = rank > 0, hi = rank < nranks - 1;
     const long top = nn - plane;
+    if (use_p2p) {
+      ++seq_halo;
+      unsigned blocks = (unsigned)std::min<long>((3 * plane + 255) / 256, 148);
+      k_halo_p2p<<<blocks, 256, 0, stream>>>(v, mailbox.d, lo ? peers.p[rank - 1] : nullptr, hi ? peers.p[rank + 1] : nullptr,
+                                             nn, plane, seq_halo);
+      ++g_host_launches;
+      ++n_halo;
+      return;
+    }
     if (lo) k_plane_pack<<<nb(3 * plane), 256, 0, stream>>>(v, send_lo.d, nn, 0, plane);
     if (hi) k_plane_pack<<<nb(3 * plane), 256, 0, stream>>>(v, send_hi.d, nn, top, plane);
     NCK(g_nccl.GroupStart());
@@ -311,7 +445,7 @@ class SlabComm {
     k_dot_partial<<<kRedBlocks, 256, 0, stream>>>(a, b, nn, n_owned, partial.d);
     k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, scal.d);
     g_host_launches += 2;
-    if (nranks > 1) { NCK(g_nccl.AllReduce(scal.d, scal.d, 1, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    AllReduceDevice(scal.d, 1);
     HCK(cudaMemcpyAsync(h_scal, scal.d, sizeof(double), cudaMemcpyDeviceToHost, stream));
     HCK(cudaStreamSynchronize(stream));
     return h_scal[0];
@@ -320,14 +454,26 @@ class SlabComm {
   void ReduceToDevice(double* d_out) {
     k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, d_out);
     ++g_host_launches_ref();
-    if (nranks > 1) { NCK(g_nccl.AllReduce(d_out, d_out, 1, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    AllReduceDevice(d_out, 1);
   }
   void AllReduceDevice(double* d_buf, int n) {
-    if (nranks > 1) { NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    if (nranks == 1) return;
+    ++n_allreduce;
+    if (use_p2p && n <= 8) {
+      ++seq_scal;
+      k_allreduce_p2p<<<1, 32, 0, stream>>>(d_buf, peers, rank, nranks, n, seq_scal);
+      ++g_host_launches;
+      return;
+    }
+    NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream));
   }
   // sum-reduce a small device buffer in place and fetch it
   void AllReduceFetch(double* d_buf, int n, double* h_out) {
-    if (nranks > 1) { NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    if (nranks > 1) {
+      // chunks of 8 go through the peer-memory kernel
+      if (use_p2p) { for (int o = 0; o < n; o += 8) AllReduceDevice(d_buf + o, std::min(8, n - o)); }
+      else { NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclSum, comm, stream)); ++n_allreduce; }
+    }
     HCK(cudaMemcpyAsync(h_scal, d_buf, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
     HCK(cudaStreamSynchronize(stream));
     for (int i = 0; i < n; ++i) h_out[i] = h_scal[i];
@@ -863,6 +1009,7 @@ int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_
     int nfail = 0;
     XCK(exab200_failed_points(s->ctx, s->stream, &nfail));
     if (nfail) throw Abort{"material update failed at " + std::to_string(nfail) + " quadrature points"};
+    if (s->comm.PeerError()) throw Abort{"peer-memory collective timed out waiting for a neighbour"};
     double avg[6];
     s->UpdateModel(avg);
     // x_beg = x_cur (src/mechanics_driver.cpp:907): x_beg += dt * v
@@ -963,6 +1110,17 @@ int exahost_kernel_time(exahost_sim* s, int which, double* total_ms, long* count
   return 0;
 }
 int exahost_set_tuning(exahost_sim* s, int ctas_per_sm, int variant) { return exab200_set_tuning(s->ctx, ctas_per_sm, variant); }
+
+// NVLink peer-memory collectives: every rank publishes the CUDA-IPC handle of its mailbox, the caller gathers
+// the handles of all ranks (torch.distributed) and hands them back.
+int exahost_comm_handle(exahost_sim* s, void* out64) {
+  try { HCK(cudaSetDevice(s->cfg.device)); s->comm.GetHandle(out64); return 0; }
+  catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+int exahost_set_peers(exahost_sim* s, const void* handles) {
+  try { HCK(cudaSetDevice(s->cfg.device)); s->comm.SetPeers(handles); return 0; }
+  catch (const Abort& a) { g_err = a.msg; return 1; }
+}
 
 void* exahost_stream(exahost_sim* s) { return s->stream; }
 void* exahost_ctx(exahost_sim* s) { return s->ctx; }

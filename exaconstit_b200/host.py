@@ -142,6 +142,21 @@ class VoxelSim:
                "newton_iters": 6}[name]
         return lib().exahost_counter(self._h, idx)
 
+    def enable_peer_collectives(self, dist):
+        """Switch the CG-loop exchanges from NCCL to the NVLink peer-memory kernels: all-gather the CUDA-IPC
+        handles of the ranks' mailboxes over `dist` (torch.distributed) and map them."""
+        import torch
+        if self.nranks == 1:
+            return
+        buf = (C.c_char * 64)()
+        _chk(lib().exahost_comm_handle(self._h, buf))
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(self.nranks)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(t.cpu().tolist()) for t in allh)
+        _chk(lib().exahost_set_peers(self._h, C.create_string_buffer(blob, len(blob))))
+        dist.barrier()
+
     def kernel_timing(self, enable=True):
         lib().exahost_kernel_timing(self._h, int(enable))
 

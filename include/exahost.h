@@ -50,6 +50,8 @@ int exahost_set_tuning(exahost_sim* sim, int ctas_per_sm, int variant);
 int exahost_extra_avgs(exahost_sim* sim, double* out16);
 int exahost_get(exahost_sim* sim, int which, double* h_out);
 long exahost_counter(exahost_sim* sim, int which);
+int exahost_comm_handle(exahost_sim* sim, void* out64);
+int exahost_set_peers(exahost_sim* sim, const void* handles_nranks_x64);
 void* exahost_stream(exahost_sim* sim);
 void* exahost_ctx(exahost_sim* sim);
 

@@ -29,6 +29,8 @@ inp, gold = refcases.case_inputs("voce_pa")
 sim = host.VoxelSim(inp["n"], inp["length"], inp["xtal"], inp["kin"], inp["props"], inp["temp_k"], inp["grain_ids"],
                     inp["quats"], nr=inp["nr"], kr=inp["kr"], rank=rank, nranks=world, device=local,
                     nccl_id=bytes(idt.cpu().tolist()))
+if %(p2p)d:
+    sim.enable_peer_collectives(dist)
 hist = sim.run(inp["dts"][:%(nsteps)d], inp["bcs"])
 if rank == 0:
     print("RESULT " + json.dumps(dict(stress=[h["avg_stress"].tolist() for h in hist],
@@ -39,15 +41,16 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_rank_run_matches_single_rank(tmp_path):
+@pytest.mark.parametrize("p2p", [0, 1])
+def test_two_rank_run_matches_single_rank(tmp_path, p2p):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     nsteps = 5
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % dict(root=ROOT, nsteps=nsteps))
+    script.write_text(WORKER % dict(root=ROOT, nsteps=nsteps, p2p=p2p))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(29611 + p2p), str(script)],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
