@@ -33,7 +33,7 @@ struct MatDev {
   int xtal, kin, nslip, nhist, withGAthermal, pad_;
   double P[kMaxSlip][5];
   double Q[kMaxSlip][3];
-  double Kdiag[5], bulk, gmod;
+  double Kdiag[5], bulk, gmod, Kvd;  // Kvd: hexagonal volumetric <-> c-axis deviator coupling (0 for cubic)
   double tol, gruneisen, dtde, tK0;
   // Voce power law
   double xm, gam_w0, h0, tausi, taus0, xmprime, xms, gamss0, kappa0;
@@ -284,7 +284,7 @@ template <int NSLIP>
 struct Problem {
   double dt, dt_ri, detVi, tK;
   double e_n[5], q_n[4], d_sm[5], w_sm[3];
-  double eps_si, rot_si;
+  double eps_si, rot_si, T1_shift;
   static constexpr int NG = (NSLIP == 24) ? 24 : 1;  // per-system resistances only differ for HCP families
   double g[NG], c_e[NG], gam_w, gam_r;
   // state of the last evaluation
@@ -340,6 +340,7 @@ struct Problem {
     double T[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) T[i] = m.Kdiag[i] * e_f[i];
+    T[1] += T1_shift;
     double dp[5] = {0, 0, 0, 0, 0}, wp[3] = {0, 0, 0};
     double dDp[5][5], dWp[3][5];
     if (Jac) {
@@ -644,6 +645,7 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
   prob.dt_ri = 1.0 / dt;
   prob.detVi = 1.0 / vNew;
   prob.tK = tkelv;
+  prob.T1_shift = m.Kvd * log(vNew) / sqr3;
   prob.kin_vals(m, h_u);
   const double halfVMidDt = 0.25 * (vOld + vNew) * dt;
   double dEDev = halfVMidDt * (s_svec_p[0] * d_svec_p[0] + s_svec_p[1] * d_svec_p[1] + s_svec_p[2] * d_svec_p[2] +
@@ -680,6 +682,8 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
   double sig_lat[5], sig_sm[5], s6[6];
 #pragma unroll
   for (int i = 0; i < 5; ++i) sig_lat[i] = prob.detVi * m.Kdiag[i] * prob.e_f[i];
+  sig_lat[1] += prob.detVi * prob.T1_shift;
+  const double p_tot = pEOS - m.Kvd * prob.e_f[1] * prob.detVi / sqr3;  // hexagonal: c-axis strain carries pressure
   rot_vecd<false>(prob.C, sig_lat, sig_sm);
   vecd_to_svec(sig_sm, s6);
   dEDev += halfVMidDt * (s6[0] * d_svec_p[0] + s6[1] * d_svec_p[1] + s6[2] * d_svec_p[2] +
@@ -687,7 +691,7 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
   h1[ind_int_eng] = eNew + dEDev;
   {
     double* so = stress1 + p * 6;
-    so[0] = s6[0] - pEOS; so[1] = s6[1] - pEOS; so[2] = s6[2] - pEOS;
+    so[0] = s6[0] - p_tot; so[1] = s6[1] - p_tot; so[2] = s6[2] - p_tot;
     so[3] = s6[3]; so[4] = s6[4]; so[5] = s6[5];
   }
   // ---- algorithmic tangent ----
@@ -698,7 +702,7 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
     const double xi[3] = {r_scale * x[5], r_scale * x[6], r_scale * x[7]};
     comm_Me(sig_lat, Msl);
     exp_Jr(xi, JrM);
-    double dsd[5][5];
+    double dsd[5][5], s1c[5];
     for (int c = 0; c < 5; ++c) {
       // rhs = eps_si * R5[c][:] = eps_si * (row c of R5) = eps_si * 5vec(C^T B_c C)
       double ec[5] = {0, 0, 0, 0, 0}, rhs[8];
@@ -709,6 +713,7 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
       rhs[5] = rhs[6] = rhs[7] = 0.0;
       if (ok) lu_solve8(J, piv, rhs);
       else for (int i = 0; i < 8; ++i) rhs[i] = 0.0;
+      s1c[c] = rhs[1];
       double dl[5], col[5];
       double jr[3];
 #pragma unroll
@@ -728,6 +733,19 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
                              {0, 0, 0, sqr2, 0, 0}};
     const double Bm[6][5] = {{sqr2i, -sqr6i, 0, 0, 0}, {-sqr2i, -sqr6i, 0, 0, 0}, {0, sqr2b3, 0, 0, 0},
                              {0, 0, 0, 0, sqr2i},      {0, 0, 0, sqr2i, 0},       {0, 0, sqr2i, 0, 0}};
+    double hexa[6] = {0, 0, 0, 0, 0, 0}, hexb[6] = {0, 0, 0, 0, 0, 0};
+    if (m.Kvd != 0.0) {
+      const double kc = m.Kvd * prob.detVi / sqr3;
+      for (int j = 0; j < 6; ++j) {
+        double v = 0.0;
+        for (int c = 0; c < 5; ++c) v += kc * e_scale * s1c[c] / dt * Tm[c][j];
+        hexa[j] = (j >= 3) ? 0.5 * v : v;
+      }
+      const double e1[5] = {0.0, kc, 0.0, 0.0, 0.0};
+      double e1sm[5];
+      rot_vecd<false>(prob.C, e1, e1sm);
+      vecd_to_svec(e1sm, hexb);
+    }
     double* K = matgrad + p * 36;
     for (int i = 0; i < 6; ++i)
       for (int j = 0; j < 6; ++j) {
@@ -738,8 +756,9 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const MatDev* __restr
           v += Bm[i][a] * t;
         }
         if (j >= 3) v *= 0.5;
+        if (i < 3) v += hexa[j];
         if (j < 3) {
-          v += -s6[i];
+          v += -s6[i] + hexb[i];
           if (i < 3) v += -dp_dlnV;
         }
         K[transpose ? (j * 6 + i) : (i * 6 + j)] = v;

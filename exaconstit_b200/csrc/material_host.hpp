@@ -102,6 +102,7 @@ inline std::string build_material(MatDev& m, int xtal, int kin, const double* p,
     m.Kdiag[3] = 2.0 * c44;
     m.Kdiag[4] = 2.0 * c44;
     m.bulk = (2.0 * c11 + 2.0 * c12 + 4.0 * c13 + c33) / 9.0;
+    m.Kvd = std::sqrt(2.0) * (c33 + c13 - c11 - c12) / 3.0;
     m.gmod = (2.0 * m.Kdiag[0] + m.Kdiag[1] + 2.0 * m.Kdiag[3]) / 10.0;
   } else {
     const double c11 = p[i++], c12 = p[i++], c44 = p[i++];

@@ -534,6 +534,7 @@ struct UpdateProblem {
   KinVals kv;
   double e_n[5], q_n[4], d_sm[5], w_sm[3];
   double epsdot_scale_inv, rotincr_scale_inv;
+  double T1_shift = 0.0;  // hexagonal volumetric -> c-axis deviator coupling (constant during the local solve)
   // outputs of the last evaluation
   double gdot[NSLIP_MAX], tau[NSLIP_MAX], e_f[5], q_f[4], C[9], R5[5][5];
 
@@ -574,6 +575,7 @@ struct UpdateProblem {
     double T[5], dg[NSLIP_MAX];
     const double rss_fac = m.opt.kirchhoff_rss ? 1.0 : detVi;
     for (int i = 0; i < 5; ++i) T[i] = m.Kdiag[i] * e_f[i];
+    T[1] += T1_shift;
     for (int a = 0; a < m.nslip; ++a) {
       double s = 0.0;
       for (int i = 0; i < 5; ++i) s += m.P[a][i] * T[i];
@@ -787,6 +789,7 @@ inline int get_response_sngl(const Material& m, double dt, const double* d_svec_
   prob.detVi = 1.0 / vNew;
   prob.a_V_ri = 1.0 / std::cbrt(vNew);
   prob.tK = tkelv;
+  prob.T1_shift = m.Khex_vol_dev * std::log(vNew) / sqr3;
   {
     const double dEff = vecd_Deff(prob.d_sm);
     const double wn = std::sqrt(w_vec[0] * w_vec[0] + w_vec[1] * w_vec[1] + w_vec[2] * w_vec[2]);
@@ -824,13 +827,16 @@ inline int get_response_sngl(const Material& m, double dt, const double* d_svec_
   // Cauchy stress: lattice -> sample
   double sig_lat[5], sig_sm[5];
   for (int i = 0; i < 5; ++i) sig_lat[i] = prob.detVi * m.Kdiag[i] * prob.e_f[i];
+  sig_lat[1] += prob.detVi * prob.T1_shift;
   for (int i = 0; i < 5; ++i) {
     double s = 0.0;
     for (int j = 0; j < 5; ++j) s += prob.R5[i][j] * sig_lat[j];
     sig_sm[i] = s;
   }
   vecd_to_svec(sig_sm, stress_svec_p);
-  stress_svec_p[6] = pEOS;
+  // hexagonal crystals: the c-axis deviatoric strain also carries pressure
+  const double p_cpl = -m.Khex_vol_dev * prob.e_f[1] * prob.detVi / sqr3;
+  stress_svec_p[6] = pEOS + p_cpl;
   dEDev += halfVMidDt * inner_dev(stress_svec_p, d_svec_p);
   eInt[0] = eNew + dEDev;
   sdd[0] = bulkNew;
@@ -888,6 +894,21 @@ inline int get_response_sngl(const Material& m, double dt, const double* d_svec_
         if (j >= 3) v *= 0.5;  // engineering shear
         mtanSD[i * 6 + j] = v;
       }
+    if (m.Khex_vol_dev != 0.0) {
+      // (a) pressure carried by the c-axis deviatoric strain; (b) deviatoric stress carried by the volume strain
+      const double kc = m.Khex_vol_dev * prob.detVi / sqr3;
+      for (int j = 0; j < 6; ++j) {
+        double v = 0.0;
+        for (int c = 0; c < 5; ++c) v += kc * e_scale * S[1][c] / dt * Tm[c][j];
+        if (j >= 3) v *= 0.5;
+        for (int i = 0; i < 3; ++i) mtanSD[i * 6 + j] += v;
+      }
+      double e1[5] = {0, kc, 0, 0, 0}, e1sm[5], s6b[6];
+      for (int i = 0; i < 5; ++i) { e1sm[i] = 0.0; for (int j = 0; j < 5; ++j) e1sm[i] += prob.R5[i][j] * e1[j]; }
+      vecd_to_svec(e1sm, s6b);
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 3; ++j) mtanSD[i * 6 + j] += s6b[i];
+    }
     // volumetric parts: -dp/d(eps_kk) on the diagonal block and the 1/detV dependence of sig'
     double sdev6[6];
     for (int i = 0; i < 6; ++i) sdev6[i] = stress_svec_p[i];

@@ -14,7 +14,10 @@ def make_case(n=4, seed=0, ngrains=4, xtal=0, kin=0, props=None, rate=5e-3, dt=0
     rng = np.random.default_rng(seed)
     g = refcases.goldens()
     if props is None:
-        props = g["props_cp_mts"] if kin == 2 else (g["props_cp_vocenl"] if kin == 1 else g["props_cp_voce"])
+        if xtal == 2:
+            props = refcases.hcp_props()
+        else:
+            props = g["props_cp_mts"] if kin == 2 else (g["props_cp_vocenl"] if kin == 1 else g["props_cp_voce"])
     nx = ny = nz = n
     e2n, coords = orc.voxel_mesh(nx, ny, nz)
     ne, nn = nx * ny * nz, (nx + 1) ** 3

@@ -64,3 +64,22 @@ def golden_rel_err(sim_stress, gold):
     s = np.asarray(sim_stress)[: gold.shape[0]]
     scale = np.abs(gold[:, 2:3])
     return np.abs(s - gold) / scale
+
+
+def hcp_props():
+    """Synthetic HCP (Ti-like) KMBalD property vector -- the reference ships none, so this set
+    is ours and HCP parity is oracle-vs-GPU only.  Order: rho0, cv, tol | c11 c12 c13 c33 c44 | mu_ref, T_ref |
+    c_1 x4 families (basal, prismatic, pyramidal<a>, pyramidal<c+a>) | tau_a, p, q | gam_wo, gam_ro, wrD |
+    g_0 x4 | s x4 | k1, k2_0, n^-1, gamma_o, rho_dd_ref | c/a | Gruneisen, e_ref."""
+    cv = 2.5e-3
+    return np.array([4.5e-6, cv, 1.0e-10,
+                     162.4, 92.0, 69.0, 180.7, 46.7,
+                     44.0, 300.0,
+                     1944.1, 1944.1, 2100.0, 2400.0,
+                     4.0e-4, 1.0, 1.0,
+                     1.0, 1.0, 3.0e-2,
+                     8.0e-3, 6.0e-3, 1.2e-2, 2.0e-2,
+                     1.0e-1, 1.0e-1, 1.2e-1, 1.5e-1,
+                     3.0e-4, 5.0e-5, 0.1, 1.0e-2, 9.0e-4,
+                     1.587,
+                     0.0, -cv * 300.0])

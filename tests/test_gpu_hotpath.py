@@ -27,7 +27,7 @@ def _compare(case, gpu, cpu):
     assert abs(gpu["vol"] - cpu["vol"]) / cpu["vol"] < 1e-13
 
 
-@pytest.mark.parametrize("n,xtal,kin", [(3, 0, 0), (4, 0, 0), (5, 1, 0), (4, 0, 1), (4, 1, 2), (4, 0, 2)])
+@pytest.mark.parametrize("n,xtal,kin", [(3, 0, 0), (4, 0, 0), (5, 1, 0), (4, 0, 1), (4, 1, 2), (4, 0, 2), (3, 2, 2)])
 def test_material_update_matches_oracle(n, xtal, kin):
     case = hc.make_case(n=n, seed=10 + n, ngrains=5, xtal=xtal, kin=kin)
     gpu = hc.run_gpu_hot_path(case)

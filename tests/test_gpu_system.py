@@ -96,3 +96,24 @@ def test_cyclic_bc_reversal_matches_golden():
     sim.close()
     s = np.array([h["avg_stress"] for h in hist])
     assert np.abs(s[:, 2] - gold[:n, 2]).max() / np.abs(gold[:n, 2]).max() < 3e-5
+
+
+def test_bbar_ea_nrls_system_run_matches_oracle(orc):
+    """Production-style solver settings of config 5 (workflows/Stage3 options_master.toml:83-106): B-bar
+    integration, element assembly, Newton with line search -- GPU host layer vs the CPU oracle (no golden)."""
+    from exaconstit_b200 import host
+    inp, _ = refcases.case_inputs("voce_pa")
+    n = 4
+    kw = dict(assembly=1, integ=1, nl_solver=1)
+    sim = host.VoxelSim(inp["n"], inp["length"], inp["xtal"], inp["kin"], inp["props"], inp["temp_k"],
+                        inp["grain_ids"], inp["quats"], nr=inp["nr"], kr=inp["kr"], **kw)
+    hist = sim.run(inp["dts"][:n], inp["bcs"])
+    sim.close()
+    inp2 = dict(inp)
+    inp2["dts"] = inp["dts"][:n]
+    inp2.update(kw)
+    ref = orc.sim_run(**inp2)
+    assert ref["rc"] == 0
+    s = np.array([h["avg_stress"] for h in hist])
+    assert (np.abs(s - ref["stress"]) / np.abs(ref["stress"][:, 2:3])).max() < 1e-8
+    assert [h["newton_iters"] for h in hist] == list(ref["iters"][:, 0])

@@ -16,9 +16,9 @@ def _hist(orc, xtal, kin, props, seed=0):
 
 
 @pytest.mark.parametrize("xtal,kin,pk", [(0, 0, "props_cp_voce"), (1, 0, "props_cp_voce"), (0, 2, "props_cp_mts"),
-                                         (1, 2, "props_cp_mts")])
+                                         (1, 2, "props_cp_mts"), (2, 2, "hcp")])
 def test_local_jacobian_matches_finite_differences(orc, xtal, kin, pk):
-    props = refcases.goldens()[pk]
+    props = refcases.hcp_props() if pk == "hcp" else refcases.goldens()[pk]
     h = _hist(orc, xtal, kin, props, seed=3)
     rng = np.random.default_rng(4)
     d = np.zeros(7)
@@ -120,3 +120,23 @@ def test_voce_hardening_saturates(orc):
     assert 17e-3 < hh[13] <= 122.4e-3 + 1e-12
     assert hh[13] > 0.12  # close to saturation after 60% strain
     assert abs(np.linalg.norm(hh[9:13]) - 1.0) < 1e-12
+
+
+def test_hcp_slip_systems_and_update(orc):
+    """HCP KMBalD (24 systems, per-family resistances; synthetic properties): the update converges, keeps the
+    quaternion normalised, yields a transversely-isotropic elastic tangent and plastic flow at large strain."""
+    props = refcases.hcp_props()
+    h = orc.hist_init(2, 2, props)
+    assert h.size == 40
+    L = 2e-3 * np.diag([-0.5, -0.5, 1.0])
+    s, hh = np.zeros(6), h
+    for _ in range(6):
+        s, hh, K = _one_point(orc, 2, 2, props, L, 0.5, s, hh)
+    assert abs(np.linalg.norm(hh[9:13]) - 1.0) < 1e-12
+    assert np.abs(hh[14:38]).sum() > 1e-4          # slip is active
+    assert s[2] > 0 and abs(s[0] - s[1]) < 1e-9 * abs(s[2])  # c-axis loading keeps the basal plane isotropic
+    s_el, _, K_el = _one_point(orc, 2, 2, props, 1e-6 * np.diag([1.0, -0.3, 0.2]), 1.0, np.zeros(6), h)
+    c11, c12, c13, c33, c44 = props[3:8]
+    Kref = np.array([[c11, c12, c13], [c12, c11, c13], [c13, c13, c33]])
+    assert np.abs(K_el[:3, :3] - Kref).max() / c11 < 1e-4
+    assert abs(K_el[3, 3] - c44) / c44 < 1e-4 and abs(K_el[5, 5] - 0.5 * (c11 - c12)) / c11 < 1e-4
