@@ -149,8 +149,9 @@ __global__ void k_xpby(double* __restrict__ d, const double* __restrict__ z, dou
 __global__ void __launch_bounds__(256) k_cg_step1(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
                                                   const double* __restrict__ z, const double* __restrict__ dinv,
                                                   const double* __restrict__ nom, const double* __restrict__ den, long nn,
-                                                  long n_owned, double* __restrict__ partial) {
+                                                  long n_owned, double* __restrict__ partial, double* __restrict__ den_next) {
   const double alpha = *nom / *den;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
   double s = 0.0;
   const long total = 3 * nn;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -182,8 +183,6 @@ __global__ void __launch_bounds__(256) k_cg_step2(double* __restrict__ d, const 
     y[i] = 0.0;
   }
 }
-// nom = betanom; den = 0 (accumulator of the next fused x^T K x)
-__global__ void k_cg_roll(double* nom, double* den, const double* betanom) { *nom = *betanom; *den = 0.0; }
 
 // y = a x + b y
 __global__ void k_axpby(double* __restrict__ y, const double* __restrict__ x, double a, double b, long n) {
@@ -298,44 +297,11 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 }
 
 // v: local L-vector; mb: my mailbox; lo/hi: peers' mailboxes (nullptr at the ends of the rank line)
-__global__ void __launch_bounds__(256) k_halo_p2p(double* __restrict__ v, double* mb, double* lo, double* hi, long nn,
-                                                  long plane, unsigned long long seq) {
-  const int par = (int)(seq & 1);
-  const long n3 = 3 * plane, top = nn - plane;
-  // push: my bottom plane -> lower neighbour's "from-hi" slot, my top plane -> upper neighbour's "from-lo" slot
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)gridDim.x * blockDim.x) {
-    const long c = i / plane, n = i - c * plane;
-    if (lo) lo[kMbHalo + (2 + par) * n3 + i] = v[c * nn + n];
-    if (hi) hi[kMbHalo + (0 + par) * n3 + i] = v[c * nn + top + n];
-  }
-  __threadfence_system();
-  __syncthreads();
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(mb);
-  if (threadIdx.x == 0) {
-    const unsigned long long prev = atomicAdd(&flags[16], 1ull);
-    if (prev == gridDim.x - 1) {
-      flags[16] = 0ull;
-      __threadfence_system();
-      if (lo) st_release_sys(reinterpret_cast<unsigned long long*>(lo) + 1, seq);  // I am the lower one's "hi"
-      if (hi) st_release_sys(reinterpret_cast<unsigned long long*>(hi) + 0, seq);  // I am the upper one's "lo"
-    }
-    if (lo) spin_until(&flags[0], seq, mb);
-    if (hi) spin_until(&flags[1], seq, mb);
-  }
-  __syncthreads();
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)gridDim.x * blockDim.x) {
-    const long c = i / plane, n = i - c * plane;
-    if (lo) v[c * nn + n] += ld_cg(&mb[kMbHalo + (0 + par) * n3 + i]);
-    if (hi) v[c * nn + top + n] += ld_cg(&mb[kMbHalo + (2 + par) * n3 + i]);
-  }
-}
-
 struct PeerTable { double* p[8]; };
 
-// in-place sum of val[0..n) over all ranks, n <= 8; one warp
-__global__ void k_allreduce_p2p(double* __restrict__ val, PeerTable peers, int rank, int nranks, int n,
-                                unsigned long long seq) {
-  const int lane = threadIdx.x;
+// one warp: in-place sum of val[0..n) over all ranks through the peers' scalar slots (rank order)
+__device__ __forceinline__ void warp_allreduce_p2p(double* val, const PeerTable& peers, int rank, int nranks, int n,
+                                                   unsigned long long seq, int lane) {
   const int par = (int)(seq & 1);
   double* mb = peers.p[rank];
   if (lane < nranks) {
@@ -348,8 +314,73 @@ __global__ void k_allreduce_p2p(double* __restrict__ val, PeerTable peers, int r
   __syncwarp();
   if (lane < n) {
     double s = 0.0;
-    for (int r = 0; r < nranks; ++r) s += ld_cg(&mb[kMbScal + (par * 8 + r) * 8 + lane]);  // rank order: deterministic
+    for (int r = 0; r < nranks; ++r) s += ld_cg(&mb[kMbScal + (par * 8 + r) * 8 + lane]);
     val[lane] = s;
+  }
+}
+
+// The last block (when ar_val != nullptr) is not part of the plane exchange: it all-reduces one scalar
+// (the CG denominator accumulated by the operator kernel) in the same launch.
+__global__ void __launch_bounds__(256) k_halo_p2p(double* __restrict__ v, double* mb, double* lo, double* hi, long nn,
+                                                  long plane, unsigned long long seq, double* ar_val, PeerTable peers,
+                                                  int rank, int nranks, unsigned long long seq_scal) {
+  const unsigned nblk = ar_val ? gridDim.x - 1 : gridDim.x;
+  if (ar_val && blockIdx.x == nblk) {
+    if (threadIdx.x < 32) warp_allreduce_p2p(ar_val, peers, rank, nranks, 1, seq_scal, threadIdx.x);
+    return;
+  }
+  const int par = (int)(seq & 1);
+  const long n3 = 3 * plane, top = nn - plane;
+  // push: my bottom plane -> lower neighbour's "from-hi" slot, my top plane -> upper neighbour's "from-lo" slot
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)nblk * blockDim.x) {
+    const long c = i / plane, n = i - c * plane;
+    if (lo) lo[kMbHalo + (2 + par) * n3 + i] = v[c * nn + n];
+    if (hi) hi[kMbHalo + (0 + par) * n3 + i] = v[c * nn + top + n];
+  }
+  __threadfence_system();
+  __syncthreads();
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(mb);
+  if (threadIdx.x == 0) {
+    const unsigned long long prev = atomicAdd(&flags[16], 1ull);
+    if (prev == nblk - 1) {
+      flags[16] = 0ull;
+      __threadfence_system();
+      if (lo) st_release_sys(reinterpret_cast<unsigned long long*>(lo) + 1, seq);  // I am the lower one's "hi"
+      if (hi) st_release_sys(reinterpret_cast<unsigned long long*>(hi) + 0, seq);  // I am the upper one's "lo"
+    }
+    if (lo) spin_until(&flags[0], seq, mb);
+    if (hi) spin_until(&flags[1], seq, mb);
+  }
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)nblk * blockDim.x) {
+    const long c = i / plane, n = i - c * plane;
+    if (lo) v[c * nn + n] += ld_cg(&mb[kMbHalo + (0 + par) * n3 + i]);
+    if (hi) v[c * nn + top + n] += ld_cg(&mb[kMbHalo + (2 + par) * n3 + i]);
+  }
+}
+
+// in-place sum of val[0..n) over all ranks, n <= 8; one warp
+__global__ void k_allreduce_p2p(double* __restrict__ val, PeerTable peers, int rank, int nranks, int n,
+                                unsigned long long seq) {
+  warp_allreduce_p2p(val, peers, rank, nranks, n, seq, threadIdx.x);
+}
+// block partial sums -> one scalar -> all-reduce, one launch
+__global__ void __launch_bounds__(256) k_reduce_allreduce_p2p(const double* __restrict__ partial, int nb, double* __restrict__ out,
+                                                              PeerTable peers, int rank, int nranks, unsigned long long seq) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += partial[i];
+  __shared__ double red[8];
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      *out = t;
+    }
+    __syncwarp();
+    warp_allreduce_p2p(out, peers, rank, nranks, 1, seq, threadIdx.x);
   }
 }
 
@@ -417,15 +448,17 @@ class SlabComm {
   }
   // Sum the partial results living on the interface planes with the z-neighbours (the role of
   // P->MultTranspose followed by P->Mult in the reference, src/mechanics_operator_ext.cpp:149,157).
-  void HaloSum(double* v) {
+  void HaloSum(double* v, double* ar_scalar = nullptr) {
     if (nranks == 1) return;
     const bool lo = rank > 0, hi = rank < nranks - 1;
     const long top = nn - plane;
     if (use_p2p) {
       ++seq_halo;
-      unsigned blocks = (unsigned)std::min<long>((3 * plane + 255) / 256, 148);
-      k_halo_p2p<<<blocks, 256, 0, stream>>>(v, mailbox.d, lo ? peers.p[rank - 1] : nullptr, hi ? peers.p[rank + 1] : nullptr,
-                                             nn, plane, seq_halo);
+      unsigned blocks = (unsigned)std::min<long>((3 * plane + 255) / 256, 140);
+      if (ar_scalar) { ++seq_scal; ++n_allreduce; }
+      k_halo_p2p<<<blocks + (ar_scalar ? 1 : 0), 256, 0, stream>>>(v, mailbox.d, lo ? peers.p[rank - 1] : nullptr,
+                                                                   hi ? peers.p[rank + 1] : nullptr, nn, plane, seq_halo,
+                                                                   ar_scalar, peers, rank, nranks, seq_scal);
       ++g_host_launches;
       ++n_halo;
       return;
@@ -439,6 +472,7 @@ class SlabComm {
     if (lo) k_plane_add<<<nb(3 * plane), 256, 0, stream>>>(v, recv_lo.d, nn, 0, plane);
     if (hi) k_plane_add<<<nb(3 * plane), 256, 0, stream>>>(v, recv_hi.d, nn, top, plane);
     ++n_halo;
+    if (ar_scalar) AllReduceDevice(ar_scalar, 1);
   }
   // global dot product over uniquely-owned dofs; blocking (returns the value on the host)
   double Dot(const double* a, const double* b) {
@@ -452,8 +486,13 @@ class SlabComm {
   }
   // partial sums -> one device scalar (+ allreduce), no host involvement
   void ReduceToDevice(double* d_out) {
-    k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, d_out);
     ++g_host_launches_ref();
+    if (nranks > 1 && use_p2p) {
+      ++seq_scal; ++n_allreduce;
+      k_reduce_allreduce_p2p<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, d_out, peers, rank, nranks, seq_scal);
+      return;
+    }
+    k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, d_out);
     AllReduceDevice(d_out, 1);
   }
   void AllReduceDevice(double* d_buf, int n) {
@@ -611,7 +650,7 @@ void GradientOperator::MultAccDot(const Vector& x, Vector& y, double* d_den) con
   op->tm_grad_mult.Begin(op->stream);
   XCK(exab200_grad_mult_ex(op->ctx, x.Read(), y.Write(), EXAB200_NO_ZERO, d_den, op->stream));
   op->tm_grad_mult.End(op->stream);
-  op->comm->HaloSum(y.Write());
+  op->comm->HaloSum(y.Write(), d_den);  // interface-plane sum + all-reduce of the denominator in one launch
   ++op->grad_mults;
 }
 void GradientOperator::LocalMult(const Vector& x, Vector& y) const {
@@ -683,7 +722,7 @@ class CGSolver {
     const long nn = n / 3;
     const GradientOperator* A = static_cast<const GradientOperator*>(oper);
     const double* dinv = prec->refresh ? prec->dinv.Read() : nullptr;  // identity smoother otherwise
-    double* d_nom = scal.d + 0; double* d_den = scal.d + 1; double* d_bet = scal.d + 2;
+    // device scalars ping-pong between iterations: {nom, betanom} in scal[0..1], denominators in scal[2..3]
     HCK(cudaMemcpyAsync(r.d, b.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
     HCK(cudaMemsetAsync(x.d, 0, sizeof(double) * n, stream));
     if (dinv) prec->Mult(r, d);
@@ -693,21 +732,24 @@ class CGSolver {
     converged = 0;
     final_iter = 0;
     if (nom <= r0) { converged = 1; return; }
-    double init[3] = {nom, 0.0, 0.0};
+    double init[4] = {nom, 0.0, 0.0, 0.0};
     HCK(cudaMemcpyAsync(scal.d, init, sizeof(init), cudaMemcpyHostToDevice, stream));
     HCK(cudaMemsetAsync(z.d, 0, sizeof(double) * n, stream));
-    A->MultAccDot(d, z, d_den);
-    comm->AllReduceDevice(d_den, 1);
+    A->MultAccDot(d, z, scal.d + 2);
     {
       double den;
-      HCK(cudaMemcpyAsync(&den, d_den, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      HCK(cudaMemcpyAsync(&den, scal.d + 2, sizeof(double), cudaMemcpyDeviceToHost, stream));
       HCK(cudaStreamSynchronize(stream));
       if (den <= 0.0 && den == 0.0) return;
     }
     int i = 1;
     final_iter = max_iter;
     for (;;) {
-      k_cg_step1<<<kRedBlocks, 256, 0, stream>>>(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, nn, comm->n_owned, comm->partial.d);
+      const int a = (i - 1) & 1;
+      double* d_nom = scal.d + a; double* d_bet = scal.d + (a ^ 1);
+      double* d_den = scal.d + 2 + a; double* d_den_next = scal.d + 2 + (a ^ 1);
+      k_cg_step1<<<kRedBlocks, 256, 0, stream>>>(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, nn, comm->n_owned, comm->partial.d,
+                                                 d_den_next);
       ++g_host_launches;
       comm->ReduceToDevice(d_bet);
       const int slot = i & 7;
@@ -717,10 +759,7 @@ class CGSolver {
       if (!last) {
         // speculative: next direction and operator apply (do not touch x, r)
         k_cg_step2<<<nb(n), 256, 0, stream>>>(d.d, r.d, dinv, z.d, d_bet, d_nom, n);
-        k_cg_roll<<<1, 1, 0, stream>>>(d_nom, d_den, d_bet);
-        ++g_host_launches;
-        A->MultAccDot(d, z, d_den);
-        comm->AllReduceDevice(d_den, 1);
+        A->MultAccDot(d, z, d_den_next);
       }
       HCK(cudaEventSynchronize(ev[slot]));
       const double betanom = h_bet[slot];
