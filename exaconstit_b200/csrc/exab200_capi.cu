@@ -45,6 +45,11 @@ struct exab200_ctx {
   long launches = 0;
   int ctas_per_sm = 2;
   int variant = 10;
+  // coordinate-rebuilt Jacobians (JX kernels): end coordinates written by setup_jacobians, valid for
+  // the Jacobian array `xend_jac` they were written with
+  double* d_xend = nullptr;
+  const double* xend_jac = nullptr;
+  int variant_jx = 26, ctas_jx = 6;  // variant_jx < 0 disables the JX path
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
@@ -77,21 +82,38 @@ static int launch_gm(exab200_ctx* c, const double* x, double* y, ElemIO io, cuda
   POST_LAUNCH(c);
   return 0;
 }
-template <int NW, int STAGES, int MODE, bool ESS>
+template <int NW, int STAGES, int MODE, bool ESS, bool JX = false>
 static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
-  constexpr int smem = NW * STAGES * kWarpStageBytes + NW * STAGES * 8;
+  constexpr int smem = NW * STAGES * (JX ? kWarpStageBytesJX : kWarpStageBytes) + NW * STAGES * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_grad_mult_pa_w<NW, STAGES, MODE, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_grad_mult_pa_w<NW, STAGES, MODE, ESS, JX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const long nwt = (c->cfg.nelems + 3) / 4;
-  long grid = (long)c->sm_count * c->ctas_per_sm;
+  long grid = (long)c->sm_count * (JX ? c->ctas_jx : c->ctas_per_sm);
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
-  k_grad_mult_pa_w<NW, STAGES, MODE, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->d_matgrad, c->d_jac, x, y, io,
-                                                                                  c->cfg.nelems, c->grad_dt, dot);
+  k_grad_mult_pa_w<NW, STAGES, MODE, ESS, JX><<<(unsigned)grid, NW * 32, smem, st>>>(c->d_matgrad, c->d_jac, x, y, io,
+                                                                                      c->cfg.nelems, c->grad_dt, dot, c->d_xend);
   POST_LAUNCH(c);
   return 0;
+}
+// L-vector apply with the Jacobians rebuilt from the end coordinates {warps per CTA, stages}
+template <bool ESS>
+static int launch_grad_mult_jx(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
+  switch (c->variant_jx) {
+    case 21: return launch_gmw<4, 3, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 22: return launch_gmw<8, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 23: return launch_gmw<4, 4, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 24: return launch_gmw<2, 3, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 25: return launch_gmw<3, 3, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 26: return launch_gmw<2, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 20: return launch_gmw<4, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 27: return launch_gmw<1, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 28: return launch_gmw<1, 3, LVEC, ESS, true>(c, x, y, io, st, dot);
+    case 29: return launch_gmw<3, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+    default: return launch_gmw<2, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+  }
 }
 template <int MODE, bool ESS>
 static int launch_grad_mult_pa(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot = nullptr) {
@@ -224,6 +246,7 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
     CK(cudaMemcpy(c->d_e2n, cfg->e2n, sizeof(int) * 8 * cfg->nelems, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&c->d_ess, cfg->nnodes));
     CK(cudaMemset(c->d_ess, 0, cfg->nnodes));
+    if (cfg->assembly == EXAB200_PA) CK(cudaMalloc(&c->d_xend, sizeof(double) * 3 * cfg->nnodes));
   }
   CK(cudaMalloc(&c->d_mat, sizeof(MatDev)));
   CK(cudaMemcpy(c->d_mat, &c->mat, sizeof(MatDev), cudaMemcpyHostToDevice));
@@ -242,16 +265,21 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_fail);
   cudaFree(c->d_mat);
   cudaFree(c->d_ea);
+  cudaFree(c->d_xend);
   delete c;
 }
 
 int exab200_num_state_vars(const exab200_ctx* c) { return c ? c->mat.nhist : -1; }
 long exab200_launch_count(const exab200_ctx* c) { return c ? c->launches : -1; }
 int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
-  if (!c || ctas_per_sm < 1 || ctas_per_sm > 8 || variant < 0 || (variant % 100) > 15 || variant > 415) return fail("bad tuning");
-  c->ctas_per_sm = ctas_per_sm;
-  c->variant = variant % 100;
+  if (!c || ctas_per_sm < 1 || ctas_per_sm > 16 || variant < 0 || variant > 499) return fail("bad tuning");
+  const int v = variant % 100;
   if (variant >= 100) c->k1_min_blocks = variant / 100;  // e.g. 210 -> K1 with 2 blocks/SM, K2 variant 10
+  if (v >= 20 && v <= 29) { c->variant_jx = v; c->ctas_jx = ctas_per_sm; return 0; }
+  if (v == 99) { c->variant_jx = -1; return 0; }  // stream J from HBM (the E-vector entry points always do)
+  if (v > 15) return fail("bad tuning");
+  c->ctas_per_sm = ctas_per_sm;
+  c->variant = v;
   return 0;
 }
 
@@ -281,7 +309,9 @@ int exab200_setup_jacobians(exab200_ctx* c, const double* d_xbeg, const double* 
                             void* stream) {
   NEED_L(c);
   ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
-  k_jacobians<<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_xbeg, d_vel, dt, d_jac, io, c->cfg.nelems);
+  k_jacobians<<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(d_xbeg, d_vel, dt, d_jac, io, c->cfg.nelems,
+                                                                             c->d_xend);
+  c->xend_jac = d_jac;
   POST_LAUNCH(c);
   return 0;
 }
@@ -372,6 +402,10 @@ int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int
     k_ea_mult<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_x_L, d_y_L, io, c->cfg.nelems, d_dot_accum);
     POST_LAUNCH(c);
     return 0;
+  }
+  if (c->variant_jx >= 0 && c->d_xend && c->xend_jac == c->d_jac) {
+    if (ess) return launch_grad_mult_jx<true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+    return launch_grad_mult_jx<false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
   }
   if (ess) return launch_grad_mult_pa<LVEC, true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
   return launch_grad_mult_pa<LVEC, false>(c, d_x_L, d_y_L, io, st, d_dot_accum);

@@ -198,19 +198,26 @@ __global__ void __launch_bounds__(EPT * 8) k_grad_mult_pa(const double* __restri
 // e2n -> x dependent-load chain never stalls the contraction.
 // ------------------------------------------------------------------------------------------
 constexpr int kWarpStageBytes = 4 * kCElemSmem + 4 * kJElemBytes;  // 11584
+constexpr int kWarpStageBytesJX = 4 * kCElemSmem;                  // 9280: matGrad only
 
-template <int NW, int STAGES, int MODE, bool ESS>
+// JX = true (LVEC only): the Jacobians are not streamed from HBM (576 B/element, 20 % of the operand bytes)
+// but rebuilt in registers from the end-of-step nodal coordinates `xend` (an L-vector, mostly L1/L2 hits)
+// with the same butterfly k_jacobians uses, i.e. bit-identical to the stored J.
+template <int NW, int STAGES, int MODE, bool ESS, bool JX>
 __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __restrict__ matgrad,
                                                             const double* __restrict__ jac,
                                                             const double* __restrict__ x, double* __restrict__ y,
                                                             ElemIO io, long nelems, double dt,
-                                                            double* __restrict__ dot_accum) {
+                                                            double* __restrict__ dot_accum,
+                                                            const double* __restrict__ xend) {
+  static_assert(!JX || MODE == LVEC, "coordinate-rebuilt Jacobians need the L-vector connectivity");
+  constexpr int SB = JX ? kWarpStageBytesJX : kWarpStageBytes;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
   const int lane = l32 & 7;  // node / quadrature point
   const int el = l32 >> 3;   // element slot in the warp's sub-tile
-  unsigned char* ring = smem_raw + (size_t)w * STAGES * kWarpStageBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NW * STAGES * kWarpStageBytes) + w * STAGES;
+  unsigned char* ring = smem_raw + (size_t)w * STAGES * SB;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NW * STAGES * SB) + w * STAGES;
   const long nwt = (nelems + 3) >> 2;                 // warp tiles
   const long stride = (long)gridDim.x * NW;
   const long wt0 = (long)blockIdx.x * NW + w;
@@ -224,14 +231,14 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
   auto issue = [&](long wt, int s) {
     const long e0 = wt << 2;
     const int ne = (int)min(4L, nelems - e0);
-    unsigned char* sc = ring + s * kWarpStageBytes;
-    if (l32 == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ne * (2 * kCHalfBytes + kJElemBytes));
+    unsigned char* sc = ring + s * SB;
+    if (l32 == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)ne * (2 * kCHalfBytes + (JX ? 0 : kJElemBytes)));
     __syncwarp();
     if (l32 < 2 * ne) {
       const int i = l32 >> 1, h = l32 & 1;
       bulk_g2s(sc + i * kCElemSmem + h * (kCHalfBytes + 16),
                reinterpret_cast<const unsigned char*>(matgrad + (e0 + i) * 288) + h * kCHalfBytes, kCHalfBytes, &full[s]);
-    } else if (l32 == 8) {
+    } else if (!JX && l32 == 8) {
       bulk_g2s(sc + 4 * kCElemSmem, jac + e0 * 72, (uint32_t)ne * kJElemBytes, &full[s]);
     }
   };
@@ -250,12 +257,14 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
     return 0;  // EVEC: the offset is recomputed from the tile index
   };
   auto evec_off = [&](long wt) -> long { return ((wt << 2) + el) * 24 + lex_to_native(lane); };
-  auto load_x = [&](int nid, long wt, unsigned& msk, double& x0, double& x1, double& x2) {
-    msk = 0; x0 = x1 = x2 = 0.0;
+  auto load_x = [&](int nid, long wt, unsigned& msk, double& x0, double& x1, double& x2, double& c0, double& c1,
+                    double& c2) {
+    msk = 0; x0 = x1 = x2 = 0.0; c0 = c1 = c2 = 0.0;
     if (nid < 0) return;
     if (MODE == LVEC) {
       if (ESS) msk = io.essmask[nid];
       x0 = x[nid]; x1 = x[io.nnodes + nid]; x2 = x[2 * io.nnodes + nid];
+      if (JX) { c0 = xend[nid]; c1 = xend[io.nnodes + nid]; c2 = xend[2 * io.nnodes + nid]; }
     } else {
       const long o = evec_off(wt);
       x0 = x[o]; x1 = x[o + 8]; x2 = x[o + 16];
@@ -263,8 +272,8 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
   };
 
   int nid_c = load_nid(wt0), nid_n = load_nid(wt0 + stride);
-  unsigned msk_c; double xc0, xc1, xc2;
-  load_x(nid_c, wt0, msk_c, xc0, xc1, xc2);
+  unsigned msk_c; double xc0, xc1, xc2, cc0, cc1, cc2;
+  load_x(nid_c, wt0, msk_c, xc0, xc1, xc2, cc0, cc1, cc2);
 
   int s = 0;
   uint32_t phase = 0;
@@ -272,25 +281,33 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
   for (long wt = wt0; wt < nwt; wt += stride) {
     // prefetch: connectivity two tiles ahead, nodal values one tile ahead
     const int nid_n2 = load_nid(wt + 2 * stride);
-    unsigned msk_n; double xn0, xn1, xn2;
-    load_x(nid_n, wt + stride, msk_n, xn0, xn1, xn2);
+    unsigned msk_n; double xn0, xn1, xn2, cn0, cn1, cn2;
+    load_x(nid_n, wt + stride, msk_n, xn0, xn1, xn2, cn0, cn1, cn2);
 
     const double u0 = (msk_c & 1) ? 0.0 : xc0, u1 = (msk_c & 2) ? 0.0 : xc1, u2 = (msk_c & 4) ? 0.0 : xc2;
     double d00, d01, d02, d10, d11, d12, d20, d21, d22;
     nodal_to_qp_grad(u0, lane, d00, d01, d02);
     nodal_to_qp_grad(u1, lane, d10, d11, d12);
     nodal_to_qp_grad(u2, lane, d20, d21, d22);
+    double J[9];
+    if (JX) {
+      nodal_to_qp_grad(cc0, lane, J[0], J[3], J[6]);
+      nodal_to_qp_grad(cc1, lane, J[1], J[4], J[7]);
+      nodal_to_qp_grad(cc2, lane, J[2], J[5], J[8]);
+    }
 
     mbar_wait(&full[s], phase);
 
     const bool active = nid_c >= 0;
     double t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0, t20 = 0, t21 = 0, t22 = 0;
     if (active) {
-      const unsigned char* sc = ring + s * kWarpStageBytes;
-      const double* Jq = reinterpret_cast<const double*>(sc + 4 * kCElemSmem + el * kJElemBytes) + lane * 9;
-      double J[9], adj[9];
+      const unsigned char* sc = ring + s * SB;
+      double adj[9];
+      if (!JX) {
+        const double* Jq = reinterpret_cast<const double*>(sc + 4 * kCElemSmem + el * kJElemBytes) + lane * 9;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+        for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+      }
       const double det = adjugate(J, adj);
       const double c = dt * kWq / det;
       const double g00 = d00 * adj[0] + d01 * adj[3] + d02 * adj[6];
@@ -347,6 +364,7 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
     }
     nid_c = nid_n; nid_n = nid_n2;
     msk_c = msk_n; xc0 = xn0; xc1 = xn1; xc2 = xn2;
+    cc0 = cn0; cc1 = cn1; cc2 = cn2;
     if (++s == STAGES) { s = 0; phase ^= 1; }
   }
   if (dot_accum) {
@@ -543,7 +561,8 @@ __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ ma
 // (src/mechanics_model.cpp:445-481) fused in.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_jacobians(const double* __restrict__ xbeg, const double* __restrict__ vel,
-                                                   double dt, double* __restrict__ jac, ElemIO io, long nelems) {
+                                                   double dt, double* __restrict__ jac, ElemIO io, long nelems,
+                                                   double* __restrict__ xend) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 7;
   const long e = gt >> 3;
@@ -553,6 +572,9 @@ __global__ void __launch_bounds__(256) k_jacobians(const double* __restrict__ xb
     const long nid = io.e2n[e * 8 + lex_to_native(lane)];
     c0 = xbeg[nid]; c1 = xbeg[io.nnodes + nid]; c2 = xbeg[2 * io.nnodes + nid];
     if (vel) { c0 += dt * vel[nid]; c1 += dt * vel[io.nnodes + nid]; c2 += dt * vel[2 * io.nnodes + nid]; }
+    // the coordinates J is built from, kept for the PA gradient apply (every element sharing the node
+    // stores the same bits)
+    if (xend) { xend[nid] = c0; xend[io.nnodes + nid] = c1; xend[2 * io.nnodes + nid] = c2; }
   }
   double J[9];
   nodal_to_qp_grad(c0, lane, J[0], J[3], J[6]);

@@ -138,9 +138,13 @@ int exab200_grad_calc(exab200_ctx* ctx, const double* d_jac, const double* d_fie
 /* Kernel launch counter (all launches issued through this context). */
 long exab200_launch_count(const exab200_ctx* ctx);
 
-/* Tuning knobs for the PA gradient apply: persistent CTAs per SM (default 1) and tile variant
- * (CTA-tile kernel 0: 16 elems x 4 stages, 1: 16x2, 2: 32x2, 3: 8x4, 4: 16x3; warp-private pipelines
- * 10: 4 warps x 2 stages (default), 11: 4x3, 12: 8x2, 13: 2x3, 14: 4x4, 15: 3x3) -- benchmarking only. */
+/* Tuning knobs for the PA gradient apply: persistent CTAs per SM and tile variant -- benchmarking only.
+ *   J streamed from HBM: CTA-tile kernel 0: 16 elems x 4 stages, 1: 16x2, 2: 32x2, 3: 8x4, 4: 16x3;
+ *     warp-private pipelines 10: 4 warps x 2 stages (default, 2 CTAs/SM), 11: 4x3, 12: 8x2, 13: 2x3, 14: 4x4, 15: 3x3;
+ *   J rebuilt in registers from the end coordinates stored by exab200_setup_jacobians (L-vector entry points, used
+ *     whenever the bound J array is the one that call wrote): 20: 4x2, 21: 4x3, 22: 8x2, 23: 4x4, 24: 2x3, 25: 3x3,
+ *     26: 2x2 (default, 6 CTAs/SM), 27: 1x2, 28: 1x3, 29: 3x2;  99: disable the rebuilt-J path.
+ *   variant + 100*k additionally sets the material-update occupancy target to k CTAs/SM. */
 int exab200_set_tuning(exab200_ctx* ctx, int ctas_per_sm, int variant);
 
 #ifdef __cplusplus

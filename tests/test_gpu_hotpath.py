@@ -170,3 +170,49 @@ def test_fused_cg_denominator(assembly):
     ctx.grad_mult_ex(x, y, flags=2, dot_accum=None)
     assert hc.rel_err(y.cpu().numpy(), 2.0 * cpu["y_grad"]) < OP_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("n,variant,ctas", [(5, 20, 3), (7, 21, 2), (6, 24, 4), (9, 26, 6)])
+def test_grad_mult_rebuilt_jacobians(n, variant, ctas):
+    """PA gradient apply with the Jacobians rebuilt in registers from the end coordinates that
+    exab200_setup_jacobians stored (the default L-vector path) against the oracle and against the same kernel
+    streaming J from HBM; after a setup_jacobians call for a different J array the library must fall back to
+    the bound J."""
+    import torch
+    from exaconstit_b200 import capi
+    case = hc.make_case(n=n, seed=40 + n, ngrains=4)
+    cpu = hc.run_oracle_hot_path(case)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    T = lambda a: torch.tensor(np.ascontiguousarray(a), **f64)
+    ne, nn, dt = case["ne"], case["nn"], case["dt"]
+    ctx = capi.Context(case["xtal"], case["kin"], case["props"], 298.0, ne, nn, case["e2n"], 0, 0)
+    ctx.set_essential_mask(case["essmask"])
+    ctx.set_tuning(ctas, variant)
+    jac = torch.empty(ne * 72, **f64)
+    ctx.setup_jacobians(T(case["xbeg"]), T(case["vel"]), dt, jac)
+    assert hc.rel_err(jac.cpu().numpy(), cpu["jac"]) < 1e-14
+    ctx.grad_setup(dt, T(cpu["matgrad"]), jac)
+    x = T(case["xvec"])
+    y_jx, y_st, y_fb = (torch.empty(3 * nn, **f64) for _ in range(3))
+    l0 = ctx.launch_count()
+    ctx.grad_mult(x, y_jx)
+    assert ctx.launch_count() == l0 + 1
+    assert hc.rel_err(y_jx.cpu().numpy(), cpu["y_grad"]) < OP_TOL
+    acc = torch.zeros(1, **f64)
+    y_acc = torch.zeros(3 * nn, **f64)
+    ctx.grad_mult_ex(x, y_acc, flags=2, dot_accum=acc)
+    xm = case["xvec"].copy()
+    xm[hc.ess_dofs(case)] = 0.0
+    ref = float(xm @ cpu["y_grad"])
+    assert abs(acc.item() - ref) / abs(ref) < 1e-12
+    ctx.set_tuning(1, 99)  # stream J
+    ctx.grad_mult(x, y_st)
+    assert hc.rel_err(y_st.cpu().numpy(), cpu["y_grad"]) < OP_TOL
+    assert ((y_jx - y_st).abs().max() / y_st.abs().max()).item() < 1e-14
+    # stale end coordinates (written for another J array) are not used
+    ctx.set_tuning(ctas, variant)
+    other = torch.empty_like(jac)
+    ctx.setup_jacobians(T(case["xbeg"]) * 1.5, None, 0.0, other)
+    ctx.grad_mult(x, y_fb)
+    assert hc.rel_err(y_fb.cpu().numpy(), cpu["y_grad"]) < OP_TOL
+    ctx.close()

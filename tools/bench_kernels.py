@@ -73,15 +73,25 @@ def main():
     ctx.grad_setup(dt, mg, jac)
     x = torch.randn(3 * nn, **f64)
     y = torch.empty_like(x)
-    cfgs = [(2, 10)]
+    # 2x: Jacobians rebuilt from the end coordinates (default 20 with 3 CTAs/SM); 1x: J streamed from HBM
+    cfgs = [(6, 26)]
     if sweep:
-        cfgs = [(2, 10), (1, 12), (2, 15)]
+        cfgs = [(6, 26), (5, 26), (3, 20), (11, 27), (8, 27), (8, 28), (6, 28), (4, 29)]
     for ctas, var in cfgs:
         ctx.set_tuning(ctas, var)
         t_med, t_min = timeit(lambda: ctx.grad_mult(x, y), iters=20, warm=3)
         gbs = ne * 3264 / t_med / 1e6
         res["grad_mult_v%d_c%d" % (var, ctas)] = dict(ms=t_med, ms_min=t_min, GBps=gbs, frac=gbs / peak)
+    y_jx = y.clone()
+    ctx.set_tuning(1, 99)  # stream J
+    for ctas, var in ([(2, 10), (1, 12), (2, 15)] if sweep else [(2, 10)]):
+        ctx.set_tuning(ctas, var)
+        t_med, t_min = timeit(lambda: ctx.grad_mult(x, y), iters=20, warm=3)
+        gbs = ne * 3264 / t_med / 1e6
+        res["grad_mult_v%d_c%d" % (var, ctas)] = dict(ms=t_med, ms_min=t_min, GBps=gbs, frac=gbs / peak)
+    print("JX vs streamed-J max rel diff:", float((y - y_jx).abs().max() / y.abs().max()))
     ctx.set_tuning(2, 10)
+    ctx.set_tuning(6, 26)
     r = torch.empty_like(x)
     t_med, _ = timeit(lambda: ctx.residual(jac, s1, r))
     res["residual"] = dict(ms=t_med, GBps=ne * 1152 / t_med / 1e6)
