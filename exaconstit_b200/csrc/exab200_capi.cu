@@ -31,7 +31,6 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct exab200_ctx {
   exab200_config cfg;
   MatDev mat;
-  MatDev* d_mat = nullptr;  // device copy read by K1
   int device = 0, sm_count = 148;
   int* d_e2n = nullptr;
   unsigned char* d_ess = nullptr;
@@ -171,29 +170,39 @@ __global__ void __launch_bounds__(256) k_grad_calc(const double* __restrict__ ja
 }
 
 
-template <int NSLIP, int MODE, int MINB>
+template <int NSLIP, int KIN, int MODE, int MINB>
 static int launch_k1(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0, const double* h0,
                      double* s1, double* h1, double* mg, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_model_setup<NSLIP, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
+    CK(cudaFuncSetAttribute(k_model_setup<NSLIP, KIN, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
     attr_set = true;
   }
   const unsigned nb = eblocks(c->cfg.nelems, kJS);
-  k_model_setup<NSLIP, MODE, MINB><<<nb, kJS, kK1SmemBytes, st>>>(c->d_mat, dt, c->cfg.temp_k, d_jac, d_vel,
-                                                                    MODE == LVEC ? c->d_e2n : nullptr, c->cfg.nnodes, s0, h0, s1,
-                                                                    h1, mg, c->cfg.nelems, 1, c->d_fail);
+  k_model_setup<NSLIP, KIN, MODE, MINB><<<nb, kJS, kK1SmemBytes, st>>>(c->mat, dt, d_jac, d_vel,
+                                                                         MODE == LVEC ? c->d_e2n : nullptr, c->cfg.nnodes, s0, h0, s1,
+                                                                         h1, mg, c->cfg.nelems, 1, c->d_fail);
   POST_LAUNCH(c);
   return 0;
 }
-template <int NSLIP, int MODE>
+template <int NSLIP, int KIN, int MODE>
 static int launch_k1_occ(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0,
                          const double* h0, double* s1, double* h1, double* mg, cudaStream_t st) {
   switch (c->k1_min_blocks) {
-    case 2: return launch_k1<NSLIP, MODE, 2>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
-    case 4: return launch_k1<NSLIP, MODE, 4>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
-    default: return launch_k1<NSLIP, MODE, 3>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+    case 2: return launch_k1<NSLIP, KIN, MODE, 2>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+    default: return launch_k1<NSLIP, KIN, MODE, 3>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
   }
+}
+template <int MODE>
+static int launch_k1_model(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0,
+                           const double* h0, double* s1, double* h1, double* mg, cudaStream_t st) {
+  const bool km = c->mat.kin == KIN_KMBALD;
+  if (c->mat.nslip == 12) {
+    if (km) return launch_k1_occ<12, 1, MODE>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+    return launch_k1_occ<12, 0, MODE>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+  }
+  if (!km) return fail("24 slip systems are only available with KMBalD kinetics");
+  return launch_k1_occ<24, 1, MODE>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
 }
 
 // The reference skips the tangent transpose for EA on a device backend (src/mechanics_ecmech.cpp:155) and then
@@ -203,12 +212,8 @@ static int model_setup_impl(exab200_ctx* c, int mode, double dt, const double* d
   if (!c) return fail("null ctx");
   if (!(dt > 0.0)) return fail("dt must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->mat.nslip == 12) {
-    if (mode == LVEC) return launch_k1_occ<12, LVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
-    return launch_k1_occ<12, EVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
-  }
-  if (mode == LVEC) return launch_k1_occ<24, LVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
-  return launch_k1_occ<24, EVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+  if (mode == LVEC) return launch_k1_model<LVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
+  return launch_k1_model<EVEC>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
 }
 
 
@@ -248,8 +253,6 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
     CK(cudaMemset(c->d_ess, 0, cfg->nnodes));
     if (cfg->assembly == EXAB200_PA) CK(cudaMalloc(&c->d_xend, sizeof(double) * 3 * cfg->nnodes));
   }
-  CK(cudaMalloc(&c->d_mat, sizeof(MatDev)));
-  CK(cudaMemcpy(c->d_mat, &c->mat, sizeof(MatDev), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_fail, sizeof(int)));
   CK(cudaMemset(c->d_fail, 0, sizeof(int)));
   if (cfg->assembly == EXAB200_EA) CK(cudaMalloc(&c->d_ea, sizeof(double) * 576 * cfg->nelems));
@@ -263,7 +266,6 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_e2n);
   cudaFree(c->d_ess);
   cudaFree(c->d_fail);
-  cudaFree(c->d_mat);
   cudaFree(c->d_ea);
   cudaFree(c->d_xend);
   delete c;

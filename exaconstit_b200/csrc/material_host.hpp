@@ -7,7 +7,7 @@
 #include <cstring>
 #include <string>
 
-#include "k_material.cuh"
+#include "material_point.hpp"
 
 namespace exab {
 
@@ -142,9 +142,20 @@ inline std::string build_material(MatDev& m, int xtal, int kin, const double* p,
   else if (xtal == XTAL_BCC) slip_bcc(m);
   else slip_hcp(m, cOverA);
   if (kin != KIN_KMBALD) {
+    m.xmi = 1.0 / m.xm;
     m.pl_t_min = std::pow(1.0e-60, m.xm);
     m.pl_t_max = std::pow(1.0e45, m.xm);
-    m.pl_max = std::exp((1.0 / m.xm - 1.0) * std::log(m.pl_t_max));
+    m.pl_max = std::exp((m.xmi - 1.0) * std::log(m.pl_t_max));
+    // integer exponent 1/m - 1 (49 for the reference's Voce sets): evaluated by repeated squaring
+    const double n = m.xmi - 1.0;
+    m.pl_n = (n >= 1.0 && n <= 512.0 && n == std::floor(n)) ? (int)n : 0;
+  }
+  // products used by the Jacobian accumulation: d D^p = sum dg P(x)P, d W^p = sum dg Q(x)P
+  for (int a = 0; a < m.nslip; ++a) {
+    for (int i = 0; i < 5; ++i)
+      for (int j = i; j < 5; ++j) m.PP[a][mat::sidx(i, j)] = m.P[a][i] * m.P[a][j];
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < 5; ++j) m.QP[a][k * 5 + j] = m.Q[a][k] * m.P[a][j];
   }
   m.ln_ovf = std::log(1.0e45);
   m.gruneisen = p[i++];

@@ -65,7 +65,7 @@ def main():
         hist0, h1 = h1, hist0
     print("failed points:", ctx.failed_points())
     res = {}
-    for mb in ((2, 3, 4) if sweep else (3,)):
+    for mb in ((2, 3) if sweep else (2,)):
         ctx.set_tuning(2, 100 * mb + 10)
         t_med, t_min = timeit(lambda: ctx.model_setup(dt, jac, vel, s0, hist0, s1, h1, mg), iters=5, warm=1)
         res["model_setup_minb%d" % mb] = dict(ms=t_med, qpt_per_s=ne * 8 / t_med * 1e3, GBps=ne * 8 * 928 / t_med / 1e6)
