@@ -22,8 +22,9 @@
 //   * integer power-law exponents (1/m - 1 = 49 for the reference's Voce parameters) are evaluated by
 //     repeated squaring for all systems at once instead of exp(n log x) per system;
 //   * the 8x8 Newton system is factored in registers (row-wise Doolittle, 36 doubles of U live) straight
-//     from the Jacobian in shared memory, which stays intact for the rarely needed dogleg quantities;
-//     a growth check falls back to the partially pivoted in-place factorisation;
+//     from the Jacobian in shared memory, which stays intact for the dogleg quantities (J^T R is accumulated
+//     while the rows pass through registers); a growth check falls back to the partially pivoted in-place
+//     factorisation;
 //   * there is a single inlined call site of the residual/Jacobian evaluation (a small state machine
 //     drives trial / re-evaluation / final passes), so the code stays inside the instruction cache.
 #pragma once
@@ -314,16 +315,21 @@ EXAB_HDN void lu_solve8(const double* A, const int* piv, double* b) {
 }
 
 // Row-wise Doolittle factorisation in registers of the (intact) matrix J, one right-hand side carried
-// along; returns false when a multiplier exceeds kGrowthMax or anything is not finite (-> pivoted path).
+// along; while the rows pass through registers the steepest-descent direction grad = J^T R is accumulated too.
+// Returns false when a multiplier exceeds kGrowthMax or anything is not finite (-> pivoted path).
 template <int JS>
-EXAB_HD bool lu_solve_reg(const double* J, double* b) {
+EXAB_HD bool lu_solve_reg(const double* J, double* b, const double* R, double* grad) {
   double U[8][8], inv[8];
   bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) grad[j] = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     double a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a[j] = J[EXAB_JIDX(i, j)];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) grad[j] += a[j] * R[i];
     double bi = b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) {
@@ -628,31 +634,31 @@ struct Point {
 };
 
 // Trust-region dogleg Newton with the reference solver's acceptance rules (oracle/ecmech_port.hpp solve_trdl),
-// organised around ONE call site of Point::eval.  Invariants: (x, R, res) is the last accepted point; the
-// shared-memory Jacobian is valid for x whenever jac_valid.  Trial points of a plain Newton step are evaluated
-// with their Jacobian (an accepted step then needs nothing else); dogleg / Cauchy trials are evaluated without
-// it, so the Jacobian at x survives a rejection, and an accepted one is followed by a Jacobian pass at the new x.
-// The last pass re-evaluates the accepted point to emit the slip rates.  Returns the number of trial
-// evaluations, negative on failure; J holds the (unfactored) Jacobian at the returned x.
+// organised around ONE call site of Point::eval.  Invariants: (x, R, res) is the last accepted point.  Every trial
+// point is evaluated with its Jacobian, so an accepted step needs nothing else; what a rejected step needs of the
+// old point (grad = J^T R, J grad, the Newton step) is formed at the start of each Newton iteration while the
+// Jacobian is still intact (the factorisation works in registers).  The last pass re-evaluates the accepted point
+// to emit the slip rates; only a failed solve needs one extra Jacobian pass before it.  Returns the number of
+// trial evaluations, negative on failure; J holds the (unfactored) Jacobian at the returned x.
 template <int NSLIP, int KIN, int JS>
 EXAB_HD int solve_point(const MatDev& m, Point<NSLIP, KIN, JS>& P, double* x, double* J, double tol, double* gout) {
   const double xiLG = 0.75, xiLO = 0.35, xiIncDelta = 1.5, xiDecDelta = 0.25;
   const double deltaMin = 1e-12, deltaMax = 1e4;
-  enum { TRIAL_J = 0, TRIAL_NOJ = 1, REJAC = 2, FINAL = 3 };
+  enum { TRIAL = 0, REJAC = 2, FINAL = 3 };
   double R[8], xt[8], Rt[8], nr[8], grad[8], Jg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { x[i] = 0.0; xt[i] = 0.0; R[i] = 0.0; nr[i] = 0.0; grad[i] = 0.0; Jg[i] = 0.0; }
   double res = 0.0, delta = 1.0e2, pred = 0.0, sn = 0.0, g2 = 0.0, Jg2 = 0.0, nrn = 1e300;
-  int nfev = 0, iters = 0, what = TRIAL_J;
-  bool first = true, failed = false, jac_valid = false, inner = false, dogleg_ready = false, have_newton = false;
+  int nfev = 0, iters = 0, what = TRIAL;
+  bool first = true, failed = false, jac_valid = false, inner = false, have_newton = false;
   for (;;) {
-    P.eval(m, xt, Rt, J, what == TRIAL_J || what == REJAC, what == FINAL ? gout : nullptr);
+    P.eval(m, xt, Rt, J, what != FINAL, what == FINAL ? gout : nullptr);
     if (what == FINAL) break;
     if (what == REJAC) {
       jac_valid = true;
       EXAB_STAT(2);
     } else {
-      EXAB_STAT(what == TRIAL_J ? 0 : 1);
+      EXAB_STAT(0);
       ++nfev;
       const double rest = norm8(Rt);
       if (first) {
@@ -672,39 +678,43 @@ EXAB_HD int solve_point(const MatDev& m, Point<NSLIP, KIN, JS>& P, double* x, do
           else if (rho < xiLO) delta = fmax(deltaMin, fmax(delta, sn) * xiDecDelta * 2.0);
           res = rest;
           inner = false;
-          dogleg_ready = false;
-          jac_valid = (what == TRIAL_J);
+          jac_valid = true;
         } else {
           delta = fmin(delta, sn) * xiDecDelta;
           EXAB_STAT(3);
           if (delta < deltaMin) failed = true;
-          if (what == TRIAL_J) jac_valid = false;  // J now holds the rejected trial point's Jacobian
+          jac_valid = false;  // J now holds the rejected trial point's Jacobian
         }
       }
     }
     // ---- next action ----
-    if (!jac_valid) {
-      what = REJAC;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xt[i] = x[i];
-      continue;
-    }
-    if (!inner && !failed) {  // start of a Newton iteration
+    if (!inner && !failed) {  // start of a Newton iteration (J is the Jacobian at x)
       if (res <= tol || iters >= 200) {
         if (res > tol) failed = true;
       } else {
         ++iters;
 #pragma unroll
         for (int i = 0; i < 8; ++i) nr[i] = -R[i];
-        have_newton = !m.force_pivot && lu_solve_reg<JS>(J, nr);
+        have_newton = !m.force_pivot && lu_solve_reg<JS>(J, nr, R, grad);
+        bool pivoted = false;
         if (!have_newton) {
           EXAB_STAT(4);
-          // pivoted fallback, destructive: form the dogleg quantities first
+          pivoted = true;
           for (int j = 0; j < 8; ++j) { double s = 0; for (int i = 0; i < 8; ++i) s += J[EXAB_JIDX(i, j)] * R[i]; grad[j] = s; }
-          for (int i = 0; i < 8; ++i) { double s = 0; for (int j = 0; j < 8; ++j) s += J[EXAB_JIDX(i, j)] * grad[j]; Jg[i] = s; }
-          g2 = 0.0; Jg2 = 0.0;
-          for (int i = 0; i < 8; ++i) { g2 += grad[i] * grad[i]; Jg2 += Jg[i] * Jg[i]; nr[i] = -R[i]; }
-          dogleg_ready = true;
+        }
+        // J grad for the Cauchy point and the linear model of a dogleg step
+        g2 = 0.0; Jg2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += J[EXAB_JIDX(i, j)] * grad[j];
+          Jg[i] = s;
+          Jg2 += s * s;
+          g2 += grad[i] * grad[i];
+        }
+        if (pivoted) {  // partially pivoted in-place factorisation (destroys J; the next trial rebuilds it)
+          for (int i = 0; i < 8; ++i) nr[i] = -R[i];
           int piv[8];
           have_newton = lu_factor8<JS>(J, piv);
           if (have_newton) lu_solve8<JS>(J, piv, nr);
@@ -718,27 +728,20 @@ EXAB_HD int solve_point(const MatDev& m, Point<NSLIP, KIN, JS>& P, double* x, do
           for (int i = 0; i < 8; ++i) xt[i] = x[i] + nr[i];
           sn = nrn;
           pred = res;
-          what = TRIAL_J;
+          what = TRIAL;
           continue;
         }
       }
     }
     if (failed || !inner) {  // converged, or gave up: emit the state of the accepted point
-      what = FINAL;
+      what = jac_valid ? FINAL : REJAC;
 #pragma unroll
       for (int i = 0; i < 8; ++i) xt[i] = x[i];
       continue;
     }
     // ---- dogleg / Cauchy step inside the trust region (Newton step too long, or a rejected trial) ----
-    if (!dogleg_ready) {
-      EXAB_STAT(5);
-      for (int j = 0; j < 8; ++j) { double s = 0; for (int i = 0; i < 8; ++i) s += J[EXAB_JIDX(i, j)] * R[i]; grad[j] = s; }
-      for (int i = 0; i < 8; ++i) { double s = 0; for (int j = 0; j < 8; ++j) s += J[EXAB_JIDX(i, j)] * grad[j]; Jg[i] = s; }
-      g2 = 0.0; Jg2 = 0.0;
-      for (int i = 0; i < 8; ++i) { g2 += grad[i] * grad[i]; Jg2 += Jg[i] * Jg[i]; }
-      dogleg_ready = true;
-    }
     {
+      EXAB_STAT(5);
       double ca, cb;  // step = -ca * grad + cb * nr
       if (have_newton && nrn <= delta) {
         ca = 0.0; cb = 1.0;
@@ -765,8 +768,7 @@ EXAB_HD int solve_point(const MatDev& m, Point<NSLIP, KIN, JS>& P, double* x, do
       double s2 = 0.0;
       for (int i = 0; i < 8; ++i) { const double st = cb * nr[i] - ca * grad[i]; xt[i] = x[i] + st; s2 += st * st; }
       sn = sqrt(s2);
-      // a destroyed Jacobian (pivoted fallback) is rebuilt by the trial pass itself
-      what = jac_valid ? TRIAL_NOJ : TRIAL_J;
+      what = TRIAL;
     }
   }
   return failed ? -nfev : nfev;

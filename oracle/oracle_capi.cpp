@@ -147,17 +147,21 @@ int orc_model_setup(int xtal, int kin, const double* props, int nprops, const do
 }
 
 // Full quasi-static simulation on a voxel mesh.  Returns 0 or the failing step.
-//   bc_* : nbc sets; set s has bc_counts[s] (id, comp, 3 vals) entries, concatenated
+//   bc_* : nbc sets; set s has bc_counts[s] (id, comp, 3 vals) entries, concatenated; comp < 0 = velocity-gradient
+//          BC; bc_vgrads (may be null): 9 per set, row-major L
 //   nr = {rel, abs, iters}, kr = {rel, abs, iters}
+//   auto_time (may be null): {on, dt_start, dt_min, dt_scale, t_final}; then nsteps must be >= ceil(t_final/dt_min)
 //   out_stress nsteps x 6; out_extra nsteps x 16 (may be null); out_iters nsteps x 2 (may be null)
-//   out_stats = {newton_iters, pcg_iters, model_setups, grad_mults, failed_points, seconds}
-int orc_sim_run(int nx, int ny, int nz, const double* len, int xtal, int kin, const double* props, int nprops,
-                double temp_k, const int* grain_ids, const double* quats, int ngrains, const double* dts,
-                int nsteps, int nbc, const int* bc_steps, const int* bc_counts, const int* bc_ids,
-                const int* bc_comps, const double* bc_vals, int assembly, int integ, int nl_solver,
-                const double* nr, const double* kr, int true_jacobi, const double* opts, int verbose,
-                double* out_stress, double* out_extra, int* out_iters, double* out_stats,
-                double* out_hist /* final hist0, may be null */, double* out_stress_qp /* final stress0 */) {
+//   out_stats = {newton_iters, pcg_iters, model_setups, grad_mults, failed_points, seconds, steps taken}
+//   out_dts (may be null): step sizes taken
+int orc_sim_run2(int nx, int ny, int nz, const double* len, int xtal, int kin, const double* props, int nprops,
+                 double temp_k, const int* grain_ids, const double* quats, int ngrains, const double* dts,
+                 int nsteps, int nbc, const int* bc_steps, const int* bc_counts, const int* bc_ids,
+                 const int* bc_comps, const double* bc_vals, const double* bc_vgrads, int assembly, int integ,
+                 int nl_solver, const double* nr, const double* kr, int true_jacobi, const double* opts, int verbose,
+                 const double* auto_time, double* out_stress, double* out_extra, int* out_iters, double* out_stats,
+                 double* out_hist /* final hist0, may be null */, double* out_stress_qp /* final stress0 */,
+                 double* out_dts) {
   SimConfig c;
   c.nx = nx; c.ny = ny; c.nz = nz;
   for (int i = 0; i < 3; ++i) c.len[i] = len[i];
@@ -176,6 +180,7 @@ int orc_sim_run(int nx, int ny, int nz, const double* len, int xtal, int kin, co
       b.comps.push_back(bc_comps[off + i]);
       for (int d = 0; d < 3; ++d) b.vals.push_back(bc_vals[3 * (off + i) + d]);
     }
+    if (bc_vgrads) b.vgrad.assign(bc_vgrads + 9 * s, bc_vgrads + 9 * s + 9);
     off += bc_counts[s];
     c.bcs.push_back(b);
   }
@@ -185,9 +190,16 @@ int orc_sim_run(int nx, int ny, int nz, const double* len, int xtal, int kin, co
   c.true_jacobi = true_jacobi != 0;
   set_opts(c.opt, opts);
   c.verbose = verbose;
+  if (auto_time && auto_time[0] != 0.0) {
+    c.auto_time.on = true;
+    c.auto_time.dt_start = auto_time[1]; c.auto_time.dt_min = auto_time[2];
+    c.auto_time.dt_scale = auto_time[3]; c.auto_time.t_final = auto_time[4];
+    if (nsteps < (int)std::ceil(c.auto_time.t_final / c.auto_time.dt_min)) return -1;
+  }
   VoxelSim sim(c);
   auto t0 = std::chrono::steady_clock::now();
-  int rc = sim.run(out_stress, out_extra, out_iters);
+  int taken = 0;
+  int rc = sim.run(out_stress, out_extra, out_iters, out_dts, &taken);
   auto t1 = std::chrono::steady_clock::now();
   if (out_stats) {
     out_stats[0] = (double)sim.stats.newton_iters;
@@ -196,6 +208,7 @@ int orc_sim_run(int nx, int ny, int nz, const double* len, int xtal, int kin, co
     out_stats[3] = (double)sim.stats.grad_mults;
     out_stats[4] = (double)sim.stats.failed_points;
     out_stats[5] = std::chrono::duration<double>(t1 - t0).count();
+    out_stats[6] = (double)taken;
   }
   if (out_hist) std::memcpy(out_hist, sim.hist0.data(), sim.hist0.size() * sizeof(double));
   if (out_stress_qp) std::memcpy(out_stress_qp, sim.stress0.data(), sim.stress0.size() * sizeof(double));

@@ -30,7 +30,7 @@ def lib():
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB)
-        _lib.orc_sim_run.restype = C.c_int
+        _lib.orc_sim_run2.restype = C.c_int
     return _lib
 
 
@@ -231,12 +231,17 @@ def local_problem(xtal, kin, props, dt, d_svec_p, w_vec, vnew, hist, tK, x, opts
 
 def sim_run(n, length, xtal, kin, props, temp_k, grain_ids, quats, dts, bcs, assembly=0, integ=0,
             nl_solver=0, nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, 1000), true_jacobi=False,
-            opts=DEFAULT_OPTS, verbose=0, want_state=False):
-    """bcs: list of (step, ids, comps, vals).  Returns dict."""
+            opts=DEFAULT_OPTS, verbose=0, want_state=False, auto_time=None):
+    """bcs: list of (step, ids, comps, vals[, vgrad 3x3]); comps < 0 = velocity-gradient BC.
+    auto_time: dict(dt_start, dt_min, dt_scale, t_final) -> Time.Auto stepping (dts is ignored).  Returns dict."""
     nx, ny, nz = n
     props = _d(props)
     grain_ids = _i(grain_ids)
     quats = _d(quats)
+    at = np.zeros(5)
+    if auto_time:
+        at[:] = [1.0, auto_time["dt_start"], auto_time["dt_min"], auto_time["dt_scale"], auto_time["t_final"]]
+        dts = np.zeros(int(np.ceil(auto_time["t_final"] / auto_time["dt_min"])))
     dts = _d(dts)
     nsteps = dts.size
     bc_steps = _i([b[0] for b in bcs])
@@ -244,21 +249,25 @@ def sim_run(n, length, xtal, kin, props, temp_k, grain_ids, quats, dts, bcs, ass
     bc_ids = _i(np.concatenate([b[1] for b in bcs]))
     bc_comps = _i(np.concatenate([b[2] for b in bcs]))
     bc_vals = _d(np.concatenate([np.asarray(b[3], dtype=float).ravel() for b in bcs]))
+    bc_vgrads = _d(np.concatenate([np.asarray(b[4], dtype=float).ravel() if len(b) > 4 else np.zeros(9) for b in bcs]))
     out_stress = np.zeros((nsteps, 6))
     out_extra = np.zeros((nsteps, 16))
     out_iters = np.zeros((nsteps, 2), dtype=np.int32)
-    out_stats = np.zeros(6)
+    out_stats = np.zeros(7)
+    out_dts = np.zeros(nsteps)
     nh = nhist(xtal, kin)
     npts = nx * ny * nz * 8
     out_hist = np.zeros(npts * nh) if want_state else None
     out_sq = np.zeros(npts * 6) if want_state else None
     o = _d(opts)
-    rc = lib().orc_sim_run(nx, ny, nz, _p(_d(length)), xtal, kin, _p(props), props.size, C.c_double(temp_k),
-                           _p(grain_ids), _p(quats), quats.size // 4, _p(dts), nsteps, len(bcs), _p(bc_steps),
-                           _p(bc_counts), _p(bc_ids), _p(bc_comps), _p(bc_vals), assembly, integ, nl_solver,
-                           _p(_d(nr)), _p(_d(kr)), int(true_jacobi), _p(o), verbose, _p(out_stress),
-                           _p(out_extra), _p(out_iters), _p(out_stats), _p(out_hist), _p(out_sq))
-    return dict(rc=rc, stress=out_stress, extra=out_extra, iters=out_iters,
+    rc = lib().orc_sim_run2(nx, ny, nz, _p(_d(length)), xtal, kin, _p(props), props.size, C.c_double(temp_k),
+                            _p(grain_ids), _p(quats), quats.size // 4, _p(dts), nsteps, len(bcs), _p(bc_steps),
+                            _p(bc_counts), _p(bc_ids), _p(bc_comps), _p(bc_vals), _p(bc_vgrads), assembly, integ,
+                            nl_solver, _p(_d(nr)), _p(_d(kr)), int(true_jacobi), _p(o), verbose, _p(at),
+                            _p(out_stress), _p(out_extra), _p(out_iters), _p(out_stats), _p(out_hist), _p(out_sq),
+                            _p(out_dts))
+    taken = int(out_stats[6]) if rc == 0 else nsteps
+    return dict(rc=rc, stress=out_stress[:taken], extra=out_extra[:taken], iters=out_iters[:taken], dts=out_dts[:taken],
                 stats=dict(newton_iters=int(out_stats[0]), pcg_iters=int(out_stats[1]),
                            model_setups=int(out_stats[2]), grad_mults=int(out_stats[3]),
                            failed_points=int(out_stats[4]), seconds=float(out_stats[5])),

@@ -28,8 +28,15 @@ using dvec = std::vector<double>;
 struct BCSet {
   int step;                // 1-based step at which this set becomes active
   std::vector<int> ids;    // boundary attributes: 1 z_min 2 x_min 3 y_min 4 z_max 5 x_max 6 y_max
-  std::vector<int> comps;  // component codes (src/BCData.cpp:27-117)
+  std::vector<int> comps;  // component codes (src/BCData.cpp:27-117); negative = velocity-gradient BC
   dvec vals;               // 3 per id
+  dvec vgrad;              // 9, row-major L (BCs.essential_vel_grad, src/option_parser.cpp:216-226); empty if unused
+};
+
+// Time.Auto (src/option_parser.cpp, src/system_driver.cpp:225-274, src/mechanics_driver.cpp:212,845-848)
+struct AutoTime {
+  bool on = false;
+  double dt_start = 1.0, dt_min = 1.0, dt_scale = 0.25, t_final = 1.0;
 };
 
 struct SimConfig {
@@ -52,6 +59,7 @@ struct SimConfig {
   bool true_jacobi = false;  // false = reference behaviour (dinv never refreshed, quirk C.1)
   ecm::Options opt;
   int verbose = 0;
+  AutoTime auto_time;
 };
 
 struct SimStats {
@@ -150,6 +158,9 @@ class VoxelSim {
   dvec stress0, stress1, hist0, hist1, matgrad;
   dvec jac, velE, c81, D81, ea, eds, dres;
   std::vector<char> ess;    // per true dof
+  std::vector<char> ess_vg; // essential dofs driven by the velocity gradient
+  double vgradL[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool has_vgrad = false;
   dvec ess_val;             // velocity value on essential dofs
   std::vector<std::vector<int>> n2e;  // node -> (elem*8+local) list, for race-free scatter
   double dt = 0.0;
@@ -195,6 +206,7 @@ class VoxelSim {
       }
     }
     ess.assign(ndof, 0);
+    ess_vg.assign(ndof, 0);
     ess_val.assign(ndof, 0.0);
     n2e.resize(nn);
     for (long e = 0; e < ne; ++e)
@@ -219,20 +231,48 @@ class VoxelSim {
   // UpdateEssBdr + the essential-dof list (src/system_driver.cpp:321-324)
   void set_bcs(const BCSet& b) {
     std::fill(ess.begin(), ess.end(), 0);
+    std::fill(ess_vg.begin(), ess_vg.end(), 0);
     std::fill(ess_val.begin(), ess_val.end(), 0.0);
-    for (size_t s = 0; s < b.ids.size(); ++s) {
-      const int code = std::abs(b.comps[s]);
-      const bool cmp[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
-      for (long n = 0; n < nn; ++n)
-        if (on_face(n, b.ids[s]))
-          for (int d = 0; d < 3; ++d)
-            if (cmp[code][d]) { ess[d * nn + n] = 1; ess_val[d * nn + n] = b.vals[3 * s + d]; }
-    }
+    has_vgrad = false;
+    for (int i = 0; i < 9; ++i) vgradL[i] = (b.vgrad.size() == 9) ? b.vgrad[i] : 0.0;
+    // ess_vel attributes first, then ess_vgrad ones (BCManager::updateBCData, src/BCManager.cpp:10-140): a dof
+    // claimed by both kinds ends up velocity-gradient driven (UpdateVelocity applies that block last)
+    for (int pass = 0; pass < 2; ++pass)
+      for (size_t s = 0; s < b.ids.size(); ++s) {
+        const bool vg = b.comps[s] < 0;
+        if (vg != (pass == 1)) continue;
+        const int code = std::abs(b.comps[s]);
+        const bool cmp[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
+        for (long n = 0; n < nn; ++n)
+          if (on_face(n, b.ids[s]))
+            for (int d = 0; d < 3; ++d)
+              if (cmp[code][d]) {
+                ess[d * nn + n] = 1;
+                if (vg) { ess_vg[d * nn + n] = 1; has_vgrad = true; }
+                else ess_val[d * nn + n] = b.vals[3 * s + d];
+              }
+      }
   }
-  // UpdateVelocity (src/system_driver.cpp:327-333): essential components overwritten
+  // UpdateVelocity (src/system_driver.cpp:327-427): velocity BCs overwrite their components; velocity-gradient
+  // BCs get v = L (x - x_min) on the CURRENT node coordinates (origin = component-wise minimum of the mesh,
+  // recomputed every call), i.e. a constant true strain rate
   void update_velocity(dvec& v) const {
     for (long i = 0; i < ndof; ++i)
-      if (ess[i]) v[i] = ess_val[i];
+      if (ess[i] && !ess_vg[i]) v[i] = ess_val[i];
+    if (!has_vgrad) return;
+    double org[3];
+    for (int j = 0; j < 3; ++j) {
+      double m = x_end[j * nn];
+      for (long n = 1; n < nn; ++n) m = std::min(m, x_end[j * nn + n]);
+      org[j] = m;
+    }
+    for (long n = 0; n < nn; ++n)
+      for (int d = 0; d < 3; ++d)
+        if (ess_vg[d * nn + n]) {
+          double s = 0.0;
+          for (int j = 0; j < 3; ++j) s += vgradL[3 * d + j] * (x_end[j * nn + n] - org[j]);
+          v[d * nn + n] = s;
+        }
   }
 
   void scatter(const dvec& yE, dvec& yL) const {
@@ -428,12 +468,20 @@ class VoxelSim {
     if (avg) for (int c = 0; c < vdim; ++c) out[c] /= vol;
   }
 
-  // main time loop; avg_stress: nsteps x 6
-  int run(double* avg_stress, double* extra /* nsteps x 16 or null */, int* iters /* nsteps x 2 or null */) {
+  // main time loop; avg_stress: nsteps x 6.  With Time.Auto the step count is ceil(t_final / dt_min) at most
+  // (src/mechanics_driver.cpp:212) and the loop stops at the last step; out_dts (may be null) receives the step
+  // sizes actually taken, *out_nsteps their number.
+  int run(double* avg_stress, double* extra /* nsteps x 16 or null */, int* iters /* nsteps x 2 or null */,
+          double* out_dts = nullptr, int* out_nsteps = nullptr) {
     dvec v(ndof, 0.0), vprev(ndof, 0.0);
-    const int nsteps = (int)cfg.dts.size();
+    const AutoTime& at = cfg.auto_time;
+    const int nsteps = at.on ? (int)std::ceil(at.t_final / at.dt_min) : (int)cfg.dts.size();
+    double t = 0.0, dt_class = at.dt_start;
+    if (out_nsteps) *out_nsteps = 0;
     for (int ti = 1; ti <= nsteps; ++ti) {
-      dt = cfg.dts[ti - 1];
+      dt = at.on ? std::min(dt_class, at.t_final - t) : cfg.dts[ti - 1];
+      t += dt;
+      bool last_step = at.on && std::fabs(t - at.t_final) <= std::fabs(1e-3 * dt);
       const long pcg0 = stats.pcg_iters;
       for (const BCSet& b : cfg.bcs)
         if (b.step == ti) {
@@ -444,9 +492,35 @@ class VoxelSim {
         }
       update_velocity(v);
       int nit = 0;
-      bool ok = newton(v, &nit);
-      if (cfg.verbose) std::printf("step %d: newton its %d converged %d\n", ti, nit, (int)ok);
+      bool ok;
+      if (at.on) {
+        // SystemDriver::Solve, auto_time branch (src/system_driver.cpp:225-274)
+        if (last_step) dt_class = dt;
+        const double dt_old = dt_class;
+        const dvec vsave(v);
+        ok = newton(v, &nit);
+        if (!ok) {
+          for (int retry = 0; !ok && retry < 2; ++retry) {
+            v = vsave;
+            dt_class *= at.dt_scale;
+            if (dt_class < at.dt_min) dt_class = at.dt_min;
+            dt = dt_class;
+            ok = newton(v, &nit);
+          }
+          t = t - dt_old + dt_class;
+          last_step = std::fabs(t - at.t_final) <= std::fabs(1e-3 * dt);
+        }
+        const double factor = ((double)cfg.nr_iter * at.dt_scale) / (double)nit;
+        if (out_dts) out_dts[ti - 1] = dt;
+        dt_class *= factor;
+        if (dt_class < at.dt_min) dt_class = at.dt_min;
+      } else {
+        ok = newton(v, &nit);
+        if (out_dts) out_dts[ti - 1] = dt;
+      }
+      if (cfg.verbose) std::printf("step %d: t %.6f dt %.6f newton its %d converged %d\n", ti, t, dt, nit, (int)ok);
       if (!ok) return ti;
+      if (out_nsteps) *out_nsteps = ti;
       // UpdateModel: swap begin/end, then averages over the end-of-step (current) mesh
       stress0.swap(stress1);
       hist0.swap(hist1);
@@ -476,6 +550,7 @@ class VoxelSim {
         vol_avg(dp, 6, &ex[1], true);
       }
       if (iters) { iters[(ti - 1) * 2] = nit; iters[(ti - 1) * 2 + 1] = (int)(stats.pcg_iters - pcg0); }
+      if (last_step) break;
     }
     return 0;
   }

@@ -67,8 +67,8 @@ long hostcheck_model_setup(int xtal, int kin, const double* props, int nprops, i
   if (!km) return -1;
   return run<24, 1>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum);
 }
-// solver path counters since the last call: 0 trial evaluations with Jacobian, 1 without (dogleg/Cauchy steps),
-// 2 Jacobian re-evaluations, 3 rejected trials, 4 pivoted-LU fallbacks in the Newton loop, 5 dogleg set-ups,
+// solver path counters since the last call: 0 trial evaluations, 1 unused, 2 Jacobian re-evaluations (failed
+// solves only), 3 rejected trials, 4 pivoted-LU fallbacks in the Newton loop, 5 dogleg / Cauchy steps,
 // 6 pivoted-LU fallbacks in the tangent
 void hostcheck_stats(long* out8) {
   for (int i = 0; i < 8; ++i) { out8[i] = g_point_stats[i]; g_point_stats[i] = 0; }

@@ -46,8 +46,38 @@ def cyclic_bcs(rate=0.001):
     return out
 
 
+def cyclic_cs_bcs(rate=0.001, mixed=False):
+    """test/data/voce_full_cyclic_cs.toml:45-79 (all four attributes velocity-gradient driven, comps -3,-1,-2,-3)
+    and voce_full_cyclic_csm.toml:65-91 (z_min as a plain velocity BC, the rest velocity-gradient driven)."""
+    out = []
+    for step, sgn in zip([1, 11, 31, 51, 71], [1, -1, 1, -1, 1]):
+        L = [[0, 0, 0], [0, 0, 0], [0, 0, sgn * rate]]
+        comps = [3, -1, -2, -3] if mixed else [-3, -1, -2, -3]
+        out.append((step, [1, 2, 3, 4], comps, [[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, sgn * rate]], L))
+    return out
+
+
+# Time.Auto of test/data/mtsdd_full_auto.toml:102-120
+MTSDD_AUTO_TIME = dict(dt_start=0.1, dt_min=0.05, dt_scale=0.333333, t_final=10.0)
+
+
 def case_inputs(name):
     g = goldens()
+    base = dict(n=(10, 10, 10), length=(1.0, 1.0, 1.0), temp_k=298.0, grain_ids=refined_grain_ids(), quats=g["voce_quats"])
+    if name in ("voce_full_cyclic_cs", "voce_full_cyclic_csm"):
+        return dict(base, xtal=0, kin=0, props=g["props_cp_voce"], dts=np.full(70, 0.1),
+                    bcs=cyclic_cs_bcs(mixed=name.endswith("csm")), assembly=0, nr=(5e-5, 5e-10, 25),
+                    kr=(1e-7, 1e-27, 1000)), g[name + "_stress"]
+    if name == "voce_ea_cs":
+        # voce_ea.toml with constant_strain_rate: comps -3,-1,-2,-3 and essential_vel_grad diag(0,0,1e-3)
+        bcs = [(1, [1, 2, 3, 4], [-3, -1, -2, -3], np.zeros((4, 3)), [[0, 0, 0], [0, 0, 0], [0, 0, 0.001]])]
+        return dict(base, xtal=0, kin=0, props=g["props_cp_voce"], dts=g["custom_dt"], bcs=bcs, assembly=1,
+                    nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, 1000)), g["voce_ea_cs_stress"]
+    if name == "mtsdd_full_auto":
+        # compression at -1e-3, IN625 property set, automatic time stepping; FULL assembly run as PA here
+        return dict(base, xtal=0, kin=2, props=g["props_cp_mts_in625"], dts=np.zeros(0), bcs=uniaxial_bcs(-0.001),
+                    assembly=0, nr=(1e-5, 1e-12, 25), kr=(1e-7, 1e-27, 250), auto_time=dict(MTSDD_AUTO_TIME)), \
+            g["mtsdd_full_auto_stress"]
     if name == "voce_full_cyclic":
         # Time.Fixed dt = 0.1, t_final = 7.0 (voce_full_cyclic.toml:100-103); FULL assembly run as PA here
         return dict(n=(10, 10, 10), length=(1.0, 1.0, 1.0), xtal=0, kin=0, props=g["props_cp_voce"], temp_k=298.0,

@@ -61,3 +61,34 @@ def test_cyclic_reversal(orc):
     assert r["rc"] == 0
     err = np.abs(r["stress"][:, 2] - gold[:14, 2]).max() / np.abs(gold[:14, 2]).max()
     assert err < 3e-5, err
+
+
+def test_constant_strain_rate_bcs(orc):
+    """voce_ea_cs_stress.txt: velocity-gradient ("constant strain rate") boundary conditions, EA assembly."""
+    r, gold = _run(orc, "voce_ea_cs", 8)
+    _check(r, gold)
+
+
+@pytest.mark.parametrize("name", ["voce_full_cyclic_cs", "voce_full_cyclic_csm"])
+def test_cyclic_constant_strain_rate(orc, name):
+    """velocity-gradient BCs (all faces / mixed with a velocity BC) across the first load reversal"""
+    inp, gold = refcases.case_inputs(name)
+    inp["dts"] = inp["dts"][:13]
+    r = orc.sim_run(**inp)
+    assert r["rc"] == 0
+    err = np.abs(r["stress"][:, 2] - gold[:13, 2]).max() / np.abs(gold[:13, 2]).max()
+    assert err < 3e-5, err
+
+
+def test_auto_time_stepping(orc):
+    """mtsdd_full_auto_stress.txt: Time.Auto (dt grows/shrinks with the Newton iteration count), compression,
+    IN625 KMBalD parameters.  The golden has one row per accepted step; a prefix is compared."""
+    inp, gold = refcases.case_inputs("mtsdd_full_auto")
+    inp["auto_time"]["t_final"] = 1.2   # first steps of the same schedule
+    r = orc.sim_run(**inp)
+    assert r["rc"] == 0
+    n = r["stress"].shape[0]
+    assert n >= 6
+    err = np.abs(r["stress"] - gold[:n]) / np.abs(gold[:n, 2:3])
+    # the last step of the shortened run is clipped to t_final and has no golden counterpart
+    assert err[:-1].max() < TOL, err[:-1].max()

@@ -47,7 +47,7 @@ def run_host_point_update(case, force_pivot=0, disable_powi=0):
                                         C.c_double(c["dt"]), _p(jac), _p(G), _p(velE), _p(c["stress0"]), _p(c["hist0"]),
                                         _p(s1), _p(h1), _p(mg), C.byref(nfev))
     lib().hostcheck_stats(st)
-    names = ("trial_jac", "trial_nojac", "rejac", "rejected", "pivot_loop", "dogleg", "pivot_tangent")
+    names = ("trials", "unused", "rejac", "rejected", "pivot_loop", "dogleg", "pivot_tangent")
     return dict(nfail=nfail, stress1=s1, hist1=h1, matgrad=mg, nfev=nfev.value, stats=dict(zip(names, list(st))))
 
 
@@ -89,10 +89,10 @@ def test_point_update_alternate_paths(force_pivot, disable_powi):
 
 @pytest.mark.parametrize("xtal,kin,rate,dt", [(0, 0, 5e-2, 0.5), (0, 0, 1.0, 0.1), (2, 2, 2e-2, 1.0)])
 def test_point_update_dogleg_paths(xtal, kin, rate, dt):
-    """large increments: the trust region is active (dogleg / Cauchy steps, rejected trials, Jacobian re-evaluations)"""
+    """large increments: the trust region is active (dogleg / Cauchy steps, rejected trials)"""
     case = hc.make_case(n=3, seed=5, ngrains=4, xtal=xtal, kin=kin, rate=rate, dt=dt)
     cpu = hc.run_oracle_hot_path(case)
     out = run_host_point_update(case)
     _check(case, out, cpu, tol=1e-10)
     st = out["stats"]
-    assert st["trial_nojac"] > 0 and st["rejac"] > 0 and st["rejected"] > 0 and st["dogleg"] > 0
+    assert st["rejected"] > 0 and st["dogleg"] > 0 and st["trials"] == out["nfev"]
