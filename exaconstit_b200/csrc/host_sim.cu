@@ -227,6 +227,57 @@ __global__ void k_plane_pack(const double* __restrict__ v, double* __restrict__ 
   const long c = i / plane, n = i - c * plane;
   buf[i] = v[c * nn + off + n];
 }
+// component-wise minimum of a byNODES L-vector: partial[c*gridDim.x + blk], then out[c]
+__global__ void __launch_bounds__(256) k_min3_partial(const double* __restrict__ x, long nn, double* __restrict__ partial) {
+  __shared__ double red[8];
+  for (int c = 0; c < 3; ++c) {
+    double m = 1.0e300;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += (long)gridDim.x * blockDim.x) m = fmin(m, x[c * nn + i]);
+    for (int k = 16; k > 0; k >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = red[0];
+      for (int w = 1; w < 8; ++w) t = fmin(t, red[w]);
+      partial[c * gridDim.x + blockIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_min3_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+  __shared__ double red[8];
+  for (int c = 0; c < 3; ++c) {
+    double m = 1.0e300;
+    for (int i = threadIdx.x; i < nb; i += 256) m = fmin(m, partial[c * nb + i]);
+    for (int k = 16; k > 0; k >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = red[0];
+      for (int w = 1; w < 8; ++w) t = fmin(t, red[w]);
+      out[c] = t;
+    }
+    __syncthreads();
+  }
+}
+// velocity-gradient BC (src/system_driver.cpp:404-426): v_d = sum_j L(d,j) (x_j - origin_j) on the marked dofs
+struct VGrad { double L[9]; };
+__global__ void k_vgrad_vel(double* __restrict__ v, const double* __restrict__ x, const unsigned char* __restrict__ vgmask,
+                            const double* __restrict__ origin, VGrad g, long nn) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  const unsigned m = vgmask[n];
+  if (!m) return;
+  const double r0 = x[n] - origin[0], r1 = x[nn + n] - origin[1], r2 = x[2 * nn + n] - origin[2];
+  for (int d = 0; d < 3; ++d)
+    if ((m >> d) & 1) {
+      double s = 0.0;
+      s += g.L[3 * d + 0] * r0;
+      s += g.L[3 * d + 1] * r1;
+      s += g.L[3 * d + 2] * r2;
+      v[d * nn + n] = s;
+    }
+}
 static long g_host_launches = 0;
 static inline long& g_host_launches_ref() { return g_host_launches; }
 static inline unsigned nb(long n) { ++g_host_launches; return (unsigned)((n + 255) / 256); }
@@ -494,6 +545,12 @@ class SlabComm {
     }
     k_dot_final<<<1, 256, 0, stream>>>(partial.d, kRedBlocks, d_out);
     AllReduceDevice(d_out, 1);
+  }
+  // component-wise minimum over ranks (vgrad origin, src/system_driver.cpp:399); once per step: NCCL
+  void AllReduceMinDevice(double* d_buf, int n) {
+    if (nranks == 1) return;
+    ++n_allreduce;
+    NCK(g_nccl.AllReduce(d_buf, d_buf, n, ncclDouble, ncclMin, comm, stream));
   }
   void AllReduceDevice(double* d_buf, int n) {
     if (nranks == 1) return;
@@ -856,10 +913,23 @@ struct exahost_sim {
   double* h_pinned = nullptr;  // staging for host-buffer steps
   cudaEvent_t ev[4];
   long newton_total = 0;
+  // velocity-gradient ("constant strain rate") boundary conditions
+  Vector vg_mask_dev, vg_scratch;
+  bool has_vgrad = false;
+  VGrad vgrad{};
 
-  // SystemDriver::UpdateVelocity (src/system_driver.cpp:327-333)
+  // SystemDriver::UpdateVelocity (src/system_driver.cpp:327-427): velocity BCs overwrite their components; the
+  // velocity-gradient ones get L (x - x_min) on the current coordinates, x_min = component-wise minimum of the
+  // whole mesh, recomputed every call (MPI_Allreduce MIN in the reference)
   void UpdateVelocity() {
     k_set_ess<<<nb(3 * nnodes), 256, 0, stream>>>(v_sol.d, ess_val.d, oper->ess_dev(), nnodes, 0, nullptr);
+    if (!has_vgrad) return;
+    k_min3_partial<<<kRedBlocks, 256, 0, stream>>>(x_beg.d, nnodes, vg_scratch.d + 8);
+    k_min3_final<<<1, 256, 0, stream>>>(vg_scratch.d + 8, kRedBlocks, vg_scratch.d);
+    g_host_launches += 2;
+    comm.AllReduceMinDevice(vg_scratch.d, 3);
+    k_vgrad_vel<<<nb(nnodes), 256, 0, stream>>>(v_sol.d, x_beg.d, reinterpret_cast<const unsigned char*>(vg_mask_dev.d),
+                                                vg_scratch.d, vgrad, nnodes);
   }
   // SystemDriver::SolveInit (src/system_driver.cpp:293-319)
   void SolveInit() {
@@ -1018,13 +1088,37 @@ int exahost_set_bcs(exahost_sim* s, const unsigned char* mask, const double* h_e
   } catch (const Abort& a) { g_err = a.msg; return 1; }
 }
 
+// SystemDriver::UpdateEssBdr for velocity-gradient attributes: per-node component mask of the dofs driven by
+// BCs.essential_vel_grad (row-major L); mask == NULL switches them off.  The total essential mask of
+// exahost_set_bcs must include these dofs.
+int exahost_set_vgrad(exahost_sim* s, const unsigned char* mask_vgrad, const double* L9) {
+  try {
+    HCK(cudaSetDevice(s->cfg.device));
+    s->has_vgrad = false;
+    if (!mask_vgrad) return 0;
+    s->vg_mask_dev.SetSize((s->nnodes + 7) / 8 + 1);
+    s->vg_scratch.SetSize(8 + 3 * kRedBlocks);
+    HCK(cudaMemcpy(s->vg_mask_dev.d, mask_vgrad, s->nnodes, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 9; ++i) s->vgrad.L[i] = L9[i];
+    for (long i = 0; i < s->nnodes; ++i)
+      if (mask_vgrad[i] & 7) { s->has_vgrad = true; break; }
+    if (s->comm.nranks > 1) s->has_vgrad = true;  // another rank may hold the marked faces; the MIN is collective
+    return 0;
+  } catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+
+// Time.Auto state of SystemDriver::Solve (src/system_driver.cpp:225-274)
+struct AutoCtl { double dt_class, t, dt_min, dt_scale, t_final; int last_step; };
+
 // One time step of the reference's loop (src/mechanics_driver.cpp:837-907).
 //   bc_changed: run the SolveInit corrector first (src/mechanics_driver.cpp:866-878)
 //   h_ess_val_in  (may be NULL): prescribed velocities for this step, HOST buffer, copied H2D inside the call
 //   h_vel_out     (may be NULL): converged velocity, HOST buffer, copied D2H inside the call
 //   out[16]: {newton_iters, pcg_iters, converged, model_setups, grad_mults, wall seconds, avg_stress[6],
-//             device ms of the solve (CUDA events, copies excluded), device ms end to end (copies included)}
-int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out, double* out) {
+//             device ms of the solve (CUDA events, copies excluded), device ms end to end (copies included),
+//             dt actually taken, 0}
+static int step_impl(exahost_sim* s, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out, double* out,
+                     AutoCtl* at) {
   try {
     HCK(cudaSetDevice(s->cfg.device));
     const long n = 3 * s->nnodes;
@@ -1036,6 +1130,11 @@ int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_
       HCK(cudaMemcpyAsync(s->ess_val.d, s->h_pinned, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream));
     }
     HCK(cudaEventRecord(s->ev[1], s->stream));
+    if (at) {  // src/mechanics_driver.cpp:845-855
+      dt = std::min(at->dt_class, at->t_final - at->t);
+      at->t += dt;
+      at->last_step = std::fabs(at->t - at->t_final) <= std::fabs(1e-3 * dt);
+    }
     s->model->SetModelDt(dt);
     if (bc_changed) {
       HCK(cudaMemcpyAsync(s->v_prev.d, s->v_sol.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
@@ -1043,7 +1142,33 @@ int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_
       s->SolveInit();
     }
     s->UpdateVelocity();
-    s->newton->Mult(s->v_sol);
+    int newton_iters = 0;
+    if (at) {
+      if (at->last_step) at->dt_class = dt;
+      const double dt_old = at->dt_class;
+      HCK(cudaMemcpyAsync(s->tmp.d, s->v_sol.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));  // xprev
+      s->newton->Mult(s->v_sol);
+      newton_iters += s->newton->final_iter;
+      if (!s->newton->converged) {
+        for (int retry = 0; !s->newton->converged && retry < 2; ++retry) {
+          HCK(cudaMemcpyAsync(s->v_sol.d, s->tmp.d, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
+          at->dt_class *= at->dt_scale;
+          if (at->dt_class < at->dt_min) at->dt_class = at->dt_min;
+          dt = at->dt_class;
+          s->model->SetModelDt(dt);
+          s->newton->Mult(s->v_sol);
+          newton_iters += s->newton->final_iter;
+        }
+        at->t = at->t - dt_old + at->dt_class;
+        at->last_step = std::fabs(at->t - at->t_final) <= std::fabs(1e-3 * dt);
+      }
+      const double factor = ((double)s->newton->max_iter * at->dt_scale) / (double)s->newton->final_iter;
+      at->dt_class *= factor;
+      if (at->dt_class < at->dt_min) at->dt_class = at->dt_min;
+    } else {
+      s->newton->Mult(s->v_sol);
+      newton_iters = s->newton->final_iter;
+    }
     if (!s->newton->converged) throw Abort{"Newton Solver did not converge."};  // MFEM_VERIFY, src/system_driver.cpp:287
     int nfail = 0;
     XCK(exab200_failed_points(s->ctx, s->stream, &nfail));
@@ -1069,7 +1194,9 @@ int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_
     HCK(cudaEventElapsedTime(&ms_e2e, s->ev[0], s->ev[3]));
     out[12] = ms_dev;
     out[13] = ms_e2e;
-    s->newton_total += s->newton->final_iter;
+    out[14] = dt;
+    out[15] = 0.0;
+    s->newton_total += newton_iters;
     out[0] = s->newton->final_iter;
     out[1] = (double)(s->cg->total_iters - pcg0);
     out[2] = s->newton->converged;
@@ -1079,6 +1206,21 @@ int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_
     for (int i = 0; i < 6; ++i) out[6 + i] = avg[i];
     return 0;
   } catch (const Abort& a) { g_err = a.msg; return 1; }
+}
+
+int exahost_step(exahost_sim* s, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out, double* out) {
+  return step_impl(s, dt, bc_changed, h_ess_val_in, h_vel_out, out, nullptr);
+}
+
+// Time.Auto step: ctl = {dt_class, t, dt_min, dt_scale, t_final, last_step}: dt_class / t / last_step are updated in
+// place exactly like SystemDriver::Solve + the driver loop do (src/system_driver.cpp:225-274,
+// src/mechanics_driver.cpp:845-889); out[14] = the step size taken.
+int exahost_step_auto(exahost_sim* s, double* ctl6, int bc_changed, const double* h_ess_val_in, double* h_vel_out,
+                      double* out) {
+  AutoCtl at{ctl6[0], ctl6[1], ctl6[2], ctl6[3], ctl6[4], 0};
+  const int rc = step_impl(s, 0.0, bc_changed, h_ess_val_in, h_vel_out, out, &at);
+  ctl6[0] = at.dt_class; ctl6[1] = at.t; ctl6[5] = (double)at.last_step;
+  return rc;
 }
 
 // copy quadrature state to HOST buffers (parity checks): which = 0 stress0 (6/pt), 1 matVars0 (nsv/pt), 2 v_sol, 3 x_beg

@@ -107,11 +107,19 @@ class VoxelSim:
         except Exception:
             pass
 
-    def set_bcs(self, ids, comps, vals):
-        """UpdateEssBdr: essential boundary attributes / component codes / velocities (src/BCManager.cpp)."""
+    def set_bcs(self, ids, comps, vals, vgrad=None):
+        """UpdateEssBdr: essential boundary attributes / component codes / velocities (src/BCManager.cpp); negative
+        component codes mark velocity-gradient attributes driven by the 3x3 `vgrad` (BCs.essential_vel_grad)."""
         mask, val = voxel.essential_bcs(self.nx, self.ny, self.nzl, ids, comps, vals, self.z0, self.nz)
+        vg = voxel.vgrad_mask(self.nx, self.ny, self.nzl, ids, comps, self.z0, self.nz)
+        val[np.concatenate([np.nonzero(vg & (1 << d))[0] + d * self.nnodes for d in range(3)])] = 0.0
         self._ess_val = val
         _chk(lib().exahost_set_bcs(self._h, mask.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p)))
+        if any(c < 0 for c in comps):
+            L = np.ascontiguousarray(np.asarray(vgrad, dtype=np.float64).reshape(9))
+            _chk(lib().exahost_set_vgrad(self._h, vg.ctypes.data_as(C.c_void_p), L.ctypes.data_as(C.c_void_p)))
+        else:
+            _chk(lib().exahost_set_vgrad(self._h, None, None))
         return mask, val
 
     def step(self, dt, bc_changed=False, ess_val_host=None, vel_out_host=None):
@@ -122,6 +130,15 @@ class VoxelSim:
         return dict(newton_iters=int(out[0]), pcg_iters=int(out[1]), converged=bool(out[2]), model_setups=int(out[3]),
                     grad_mults=int(out[4]), seconds=float(out[5]), avg_stress=out[6:12].copy(),
                     dev_ms=float(out[12]), e2e_ms=float(out[13]))
+
+    def step_auto(self, ctl, bc_changed=False):
+        """One Time.Auto step; ctl = np.array([dt_class, t, dt_min, dt_scale, t_final, last_step]) is updated in place."""
+        out = np.zeros(16)
+        _chk(lib().exahost_step_auto(self._h, ctl.ctypes.data_as(C.c_void_p), int(bc_changed), None, None,
+                                     out.ctypes.data_as(C.c_void_p)))
+        return dict(newton_iters=int(out[0]), pcg_iters=int(out[1]), converged=bool(out[2]), model_setups=int(out[3]),
+                    grad_mults=int(out[4]), seconds=float(out[5]), avg_stress=out[6:12].copy(),
+                    dev_ms=float(out[12]), e2e_ms=float(out[13]), dt=float(out[14]))
 
     def extra_avgs(self):
         """additional_avgs of UpdateModel: plastic-work integral, <F> (9, [t*3+i]), <D^p> (6 Voigt)."""
@@ -175,9 +192,25 @@ class VoxelSim:
             changed = False
             for b in bcs:
                 if b[0] == ti:
-                    self.set_bcs(b[1], b[2], b[3])
+                    self.set_bcs(b[1], b[2], b[3], b[4] if len(b) > 4 else None)
                     changed = True
             hist.append(self.step(float(dt), bc_changed=changed))
             if extras:
                 hist[-1].update(self.extra_avgs())
+        return hist
+
+    def run_auto(self, auto_time, bcs):
+        """The reference's time loop with Time.Auto (src/mechanics_driver.cpp:212,837-967): at most
+        ceil(t_final / dt_min) steps, stops at the last step."""
+        ctl = np.array([auto_time["dt_start"], 0.0, auto_time["dt_min"], auto_time["dt_scale"], auto_time["t_final"], 0.0])
+        hist = []
+        for ti in range(1, int(np.ceil(auto_time["t_final"] / auto_time["dt_min"])) + 1):
+            changed = False
+            for b in bcs:
+                if b[0] == ti:
+                    self.set_bcs(b[1], b[2], b[3], b[4] if len(b) > 4 else None)
+                    changed = True
+            hist.append(self.step_auto(ctl, bc_changed=changed))
+            if ctl[5] != 0.0:
+                break
         return hist

@@ -51,6 +51,21 @@ def essential_bcs(nx, ny, nz, ids, comps, vals, z0=0, nz_total=None):
     return mask, val
 
 
+def vgrad_mask(nx, ny, nz, ids, comps, z0=0, nz_total=None):
+    """Per-node mask of the components driven by a velocity-gradient BC: the attributes whose component code is
+    negative (BCs.essential_comps, src/option_parser.cpp:179-194)."""
+    nn = (nx + 1) * (ny + 1) * (nz + 1)
+    mask = np.zeros(nn, dtype=np.uint8)
+    for s, attr in enumerate(ids):
+        if comps[s] >= 0:
+            continue
+        nodes = face_nodes(nx, ny, nz, attr, z0, nz_total)
+        for d in range(3):
+            if _CMP[abs(comps[s])][d]:
+                mask[nodes] |= (1 << d)
+    return mask
+
+
 def uniaxial_mask(nx, ny, nz):
     return essential_bcs(nx, ny, nz, [1, 2, 3, 4], [3, 1, 2, 3], np.zeros((4, 3)))[0]
 

@@ -42,8 +42,14 @@ int exahost_nccl_unique_id(void* out128);
 int exahost_create(const exahost_config* cfg, exahost_sim** out);
 void exahost_destroy(exahost_sim* sim);
 int exahost_set_bcs(exahost_sim* sim, const unsigned char* mask_per_node, const double* h_ess_val_L);
+/* velocity-gradient ("constant strain rate") BCs: BCs.essential_comps < 0 + BCs.essential_vel_grad
+ * (src/system_driver.cpp:346-426); mask_vgrad_per_node bit i = component i driven by L (row-major 3x3) */
+int exahost_set_vgrad(exahost_sim* sim, const unsigned char* mask_vgrad_per_node, const double* L9);
 int exahost_step(exahost_sim* sim, double dt, int bc_changed, const double* h_ess_val_in, double* h_vel_out,
                  double* out16);
+/* Time.Auto (src/system_driver.cpp:225-274): ctl6 = {dt_class, t, dt_min, dt_scale, t_final, last_step} in/out */
+int exahost_step_auto(exahost_sim* sim, double* ctl6, int bc_changed, const double* h_ess_val_in, double* h_vel_out,
+                      double* out16);
 int exahost_kernel_timing(exahost_sim* sim, int enable);
 int exahost_kernel_time(exahost_sim* sim, int which, double* total_ms, long* count, int reset);
 int exahost_set_tuning(exahost_sim* sim, int ctas_per_sm, int variant);
