@@ -117,6 +117,9 @@ def run_ours(args):
                         rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
     if nranks > 1 and not args.nccl_only:
         sim.enable_peer_collectives(dist)
+    for tv in args.tuning:
+        c, v = tv.split(":")
+        sim.set_tuning(int(c), int(v))
     mask, ess_val = sim.set_bcs(*BC)
     ess_pinned = np.ascontiguousarray(ess_val)
     vel_out = np.zeros(3 * sim.nnodes)
@@ -180,9 +183,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "qpt_updates_per_sec": (ne_local * 8 * nranks) / (k1_ms * 1e-3) if ms_cnt else None,
             "pa_mult_GBps_per_gpu": achieved,
-            "roofline": {"kernel": "k_grad_mult_pa (PA gradient apply, incl. output memset)", "bound": "hbm",
+            "roofline": {"kernel": "k_grad_mult_pa_w<2,2,LVEC,ESS,JX> (PA gradient apply, Jacobians rebuilt from coordinates; timed with its output memset)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": TRAFFIC_NCU.get(n),
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": TRAFFIC_NCU.get(n) if nranks == 1 else None,
+                         "algorithmic_bytes_per_launch": ne_local * ALG_BYTES_PA_APPLY,
                          "launches_timed": int(gm_cnt), "avg_launch_ms": apply_ms,
                          "share_of_step": gm_ms / dev_ms},
             "model_setup": {"avg_ms": k1_ms, "calls": int(ms_cnt), "share_of_step": ms_ms / dev_ms,
@@ -319,6 +324,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-only", action="store_true", help="use NCCL for the CG-loop exchanges instead of the peer-memory kernels")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--tuning", action="append", default=[], help="ctas:variant pairs passed to exab200_set_tuning (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

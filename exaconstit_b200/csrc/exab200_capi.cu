@@ -49,6 +49,7 @@ struct exab200_ctx {
   double* d_xend = nullptr;
   const double* xend_jac = nullptr;
   int variant_jx = 26, ctas_jx = 6;  // variant_jx < 0 disables the JX path
+  int l2_hint = 1;                   // operand stream of the gradient apply marked L2 evict_first
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
@@ -93,7 +94,8 @@ static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cud
   long grid = (long)c->sm_count * (JX ? c->ctas_jx : c->ctas_per_sm);
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
   k_grad_mult_pa_w<NW, STAGES, MODE, ESS, JX><<<(unsigned)grid, NW * 32, smem, st>>>(c->d_matgrad, c->d_jac, x, y, io,
-                                                                                      c->cfg.nelems, c->grad_dt, dot, c->d_xend);
+                                                                                      c->cfg.nelems, c->grad_dt, dot, c->d_xend,
+                                                                                      c->l2_hint);
   POST_LAUNCH(c);
   return 0;
 }
@@ -278,7 +280,8 @@ int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
   const int v = variant % 100;
   if (variant >= 100) c->k1_min_blocks = variant / 100;  // e.g. 210 -> K1 with 2 blocks/SM, K2 variant 10
   if (v >= 20 && v <= 29) { c->variant_jx = v; c->ctas_jx = ctas_per_sm; return 0; }
-  if (v == 99) { c->variant_jx = -1; return 0; }  // stream J from HBM (the E-vector entry points always do)
+  if (v == 99) { c->variant_jx = -1; return 0; }
+  if (v == 98 || v == 97) { c->l2_hint = (v == 98); return 0; }  // 98 / 97: L2 evict_first hint on / off  // stream J from HBM (the E-vector entry points always do)
   if (v > 15) return fail("bad tuning");
   c->ctas_per_sm = ctas_per_sm;
   c->variant = v;

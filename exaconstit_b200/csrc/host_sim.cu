@@ -435,6 +435,59 @@ __global__ void __launch_bounds__(256) k_reduce_allreduce_p2p(const double* __re
   }
 }
 
+// CG step 1 with the reduction folded in: the last block to finish sums the block partials in a fixed order
+// (bitwise reproducible), all-reduces the scalar over the ranks through the peer mailboxes when nranks > 1 and
+// publishes betanom -- one launch instead of two per CG iteration.
+__global__ void __launch_bounds__(256) k_cg_step1_fused(double* __restrict__ x, double* __restrict__ r,
+                                                        const double* __restrict__ d, const double* __restrict__ z,
+                                                        const double* __restrict__ dinv, const double* __restrict__ nom,
+                                                        const double* __restrict__ den, long nn, long n_owned,
+                                                        double* __restrict__ partial, double* __restrict__ den_next,
+                                                        unsigned int* __restrict__ counter, double* __restrict__ d_bet,
+                                                        PeerTable peers, int rank, int nranks, unsigned long long seq) {
+  const double alpha = *nom / *den;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
+  double s = 0.0;
+  const long total = 3 * nn;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    x[i] += alpha * d[i];
+    const double rn = r[i] - alpha * z[i];
+    r[i] = rn;
+    const long c = i / nn, n = i - c * nn;
+    if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+  }
+  __shared__ double red[8];
+  __shared__ bool last;
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;  // wraps back to 0 for the next launch
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t += ld_cg(&partial[i]);
+  for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      double u = 0.0;
+      for (int w = 0; w < 8; ++w) u += red[w];
+      *d_bet = u;
+    }
+    __syncwarp();
+    if (nranks > 1) warp_allreduce_p2p(d_bet, peers, rank, nranks, 1, seq, threadIdx.x);
+  }
+}
+
 // ---------------------------------------------------------------- communicator --------------
 class SlabComm {
  public:
@@ -442,7 +495,7 @@ class SlabComm {
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;
   long nn = 0, plane = 0, n_owned = 0;
-  Vector send_lo, send_hi, recv_lo, recv_hi, partial, scal;
+  Vector send_lo, send_hi, recv_lo, recv_hi, partial, scal, counter;
   double* h_scal = nullptr;  // pinned
   long n_allreduce = 0, n_halo = 0;
   // NVLink peer-memory path
@@ -457,6 +510,8 @@ class SlabComm {
     n_owned = (rank == nranks - 1) ? nn : nn - plane;
     partial.SetSize(kRedBlocks);
     scal.SetSize(8);
+    counter.SetSize(2);
+    HCK(cudaMemset(counter.d, 0, 2 * sizeof(double)));
     HCK(cudaMallocHost(&h_scal, 64 * sizeof(double)));
     if (nranks > 1) {
       if (!g_nccl.load()) throw Abort{"NCCL library could not be loaded"};
@@ -534,6 +589,20 @@ class SlabComm {
     HCK(cudaMemcpyAsync(h_scal, scal.d, sizeof(double), cudaMemcpyDeviceToHost, stream));
     HCK(cudaStreamSynchronize(stream));
     return h_scal[0];
+  }
+  // CG step 1 + reduction (+ all-reduce) in one launch; falls back to two launches on the NCCL-only path
+  void CgStep1(double* x, double* r, const double* d, const double* z, const double* dinv, const double* d_nom,
+               const double* d_den, double* d_den_next, double* d_bet) {
+    ++g_host_launches;
+    if (nranks > 1 && !use_p2p) {
+      k_cg_step1<<<kRedBlocks, 256, 0, stream>>>(x, r, d, z, dinv, d_nom, d_den, nn, n_owned, partial.d, d_den_next);
+      ReduceToDevice(d_bet);
+      return;
+    }
+    if (nranks > 1) { ++seq_scal; ++n_allreduce; }
+    k_cg_step1_fused<<<kRedBlocks, 256, 0, stream>>>(x, r, d, z, dinv, d_nom, d_den, nn, n_owned, partial.d, d_den_next,
+                                                     reinterpret_cast<unsigned int*>(counter.d), d_bet, peers, rank,
+                                                     nranks, seq_scal);
   }
   // partial sums -> one device scalar (+ allreduce), no host involvement
   void ReduceToDevice(double* d_out) {
@@ -805,10 +874,7 @@ class CGSolver {
       const int a = (i - 1) & 1;
       double* d_nom = scal.d + a; double* d_bet = scal.d + (a ^ 1);
       double* d_den = scal.d + 2 + a; double* d_den_next = scal.d + 2 + (a ^ 1);
-      k_cg_step1<<<kRedBlocks, 256, 0, stream>>>(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, nn, comm->n_owned, comm->partial.d,
-                                                 d_den_next);
-      ++g_host_launches;
-      comm->ReduceToDevice(d_bet);
+      comm->CgStep1(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, d_den_next, d_bet);
       const int slot = i & 7;
       HCK(cudaMemcpyAsync(h_bet + slot, d_bet, sizeof(double), cudaMemcpyDeviceToHost, stream));
       HCK(cudaEventRecord(ev[slot], stream));

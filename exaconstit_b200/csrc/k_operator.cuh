@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
                                                             const double* __restrict__ x, double* __restrict__ y,
                                                             ElemIO io, long nelems, double dt,
                                                             double* __restrict__ dot_accum,
-                                                            const double* __restrict__ xend) {
+                                                            const double* __restrict__ xend, int l2_hint) {
   static_assert(!JX || MODE == LVEC, "coordinate-rebuilt Jacobians need the L-vector connectivity");
+  const uint64_t pol = l2_hint ? l2_policy_evict_first() : 0ull;
   constexpr int SB = JX ? kWarpStageBytesJX : kWarpStageBytes;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
@@ -236,10 +237,13 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
     __syncwarp();
     if (l32 < 2 * ne) {
       const int i = l32 >> 1, h = l32 & 1;
-      bulk_g2s(sc + i * kCElemSmem + h * (kCHalfBytes + 16),
-               reinterpret_cast<const unsigned char*>(matgrad + (e0 + i) * 288) + h * kCHalfBytes, kCHalfBytes, &full[s]);
+      unsigned char* dst = sc + i * kCElemSmem + h * (kCHalfBytes + 16);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(matgrad + (e0 + i) * 288) + h * kCHalfBytes;
+      if (l2_hint) bulk_g2s_hint(dst, src, kCHalfBytes, &full[s], pol);
+      else bulk_g2s(dst, src, kCHalfBytes, &full[s]);
     } else if (!JX && l32 == 8) {
-      bulk_g2s(sc + 4 * kCElemSmem, jac + e0 * 72, (uint32_t)ne * kJElemBytes, &full[s]);
+      if (l2_hint) bulk_g2s_hint(sc + 4 * kCElemSmem, jac + e0 * 72, (uint32_t)ne * kJElemBytes, &full[s], pol);
+      else bulk_g2s(sc + 4 * kCElemSmem, jac + e0 * 72, (uint32_t)ne * kJElemBytes, &full[s]);
     }
   };
   {
