@@ -92,6 +92,10 @@ def workload(n, ngrains, seed):
 
 
 def run_ours(args):
+    # libraries (NCCL prints its version banner) must not write to stdout: rank 0's stdout carries ONE JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from exaconstit_b200 import host
@@ -198,7 +202,8 @@ def run_ours(args):
         }
         if nranks == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(n, pcg / max(newton, 1), setups / max(newton, 1), budget_s=args.cpu_budget)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     sim.close()
     if nranks > 1:
         dist.destroy_process_group()
