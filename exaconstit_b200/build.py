@@ -38,4 +38,14 @@ def build_all(force=False, verbose=False):
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
+    # the application driver (`mechanics -opt options.toml`): host-only C++ on top of the two libraries
+    main_src = os.path.join(csrc, "mechanics_main.cpp")
+    if os.path.exists(main_src):
+        out = os.path.join(libdir, "mechanics")
+        if force or _stale(out, deps + [os.path.join(libdir, "libexahost.so")]):
+            cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-o", out, main_src, "-L" + libdir, "-lexahost",
+                   "-lexab200", "-Wl,-rpath,$ORIGIN"]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
     return libdir

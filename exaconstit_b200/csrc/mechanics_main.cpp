@@ -1,0 +1,218 @@
+// `mechanics -opt options.toml`: the application driver of the reference (src/mechanics_driver.cpp:100-1000)
+// for the part of its input space the hot path covers -- auto-generated voxel meshes (Mesh.type = "auto"), ExaCMech
+// crystal-plasticity models, PA / EA assembly, velocity and velocity-gradient BCs (constant or changing), custom /
+// fixed / automatic time stepping -- so that the reference's own option files and text inputs drive the B200 path
+// unchanged and the volume-averaged outputs land in the same files in the same format
+// (src/system_driver.cpp:429-558).  Host code only: everything numerical happens behind exahost.h / exab200.h.
+//
+// Differences from the reference, stated on stdout when they apply: FULL assembly (hypre) is run with the matrix-free
+// PA operator; GMRES / MINRES selections are run with the PCG solver; one process drives one GPU (multi-GPU runs go
+// through bench.py / torch.distributed).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/exab200.h"
+#include "../../include/exahost.h"
+#include "options.hpp"
+
+using namespace exaopt;
+
+namespace {
+
+// mfem::Vector::Print(out, width): entries separated by blanks, `width` per line, default stream precision
+void print_vector(std::ostream& os, const double* v, int n, int width) {
+  for (int i = 0; i < n;) {
+    os << v[i];
+    ++i;
+    if (i == n) break;
+    os << ((i % width == 0) ? '\n' : ' ');
+  }
+  os << '\n';
+}
+
+// boundary attributes of the auto mesh (src/mechanics_driver.cpp:1196-1231): 1 z_min 2 x_min 3 y_min 4 z_max 5 x_max 6 y_max
+bool on_face(long node, int attr, int nx, int ny, int nz) {
+  const long px = nx + 1, py = ny + 1;
+  const long i = node % px, j = (node / px) % py, k = node / (px * py);
+  switch (attr) {
+    case 1: return k == 0;
+    case 2: return i == 0;
+    case 3: return j == 0;
+    case 4: return k == nz;
+    case 5: return i == nx;
+    case 6: return j == ny;
+  }
+  return false;
+}
+
+void apply_bcs(exahost_sim* sim, const BCSet& b, int nx, int ny, int nz) {
+  const long nn = (long)(nx + 1) * (ny + 1) * (nz + 1);
+  std::vector<unsigned char> mask(nn, 0), vg(nn, 0);
+  std::vector<double> val(3 * nn, 0.0);
+  static const bool cmp[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}, {1, 1, 1}};
+  bool any_vg = false;
+  for (int pass = 0; pass < 2; ++pass)  // velocity attributes first, velocity-gradient ones last (src/BCManager.cpp:10-140)
+    for (size_t s = 0; s < b.ids.size(); ++s) {
+      const bool is_vg = b.comps[s] < 0;
+      if (is_vg != (pass == 1)) continue;
+      if (b.ids[s] < 1 || b.ids[s] > 6) throw Abort("BCs.essential_ids: the auto mesh has boundary attributes 1..6");
+      const int code = std::abs(b.comps[s]);
+      for (long n = 0; n < nn; ++n)
+        if (on_face(n, b.ids[s], nx, ny, nz))
+          for (int d = 0; d < 3; ++d)
+            if (cmp[code][d]) {
+              mask[n] |= (unsigned char)(1 << d);
+              if (is_vg) { vg[n] |= (unsigned char)(1 << d); val[d * nn + n] = 0.0; any_vg = true; }
+              else { vg[n] &= (unsigned char)~(1 << d); val[d * nn + n] = b.vals[3 * s + d]; }
+            }
+    }
+  if (exahost_set_bcs(sim, mask.data(), val.data())) throw Abort(exahost_last_error());
+  if (exahost_set_vgrad(sim, any_vg ? vg.data() : nullptr, any_vg ? b.vgrad.data() : nullptr)) throw Abort(exahost_last_error());
+}
+
+int run(const std::string& opt_file, bool check_only) {
+  ExaOptions o(opt_file);
+  o.parse_options();
+  std::printf("exab200 mechanics: options from %s\n", opt_file.c_str());
+  if (o.assembly == Assembly::FULL)
+    std::printf("note: Solvers.assembly = FULL (hypre) is outside the hot path; running the matrix-free PA operator\n");
+  if (o.solver != KrylovSolver::PCG)
+    std::printf("note: Solvers.Krylov.solver is not PCG; the symmetric system is solved with PCG\n");
+  // ---- text inputs ----
+  const std::vector<double> props = load_numbers(o.props_file, o.nProps, "material properties");
+  (void)load_numbers(o.state_file, o.numStateVars, "state variables");  // values are re-initialised by the model (init_state_vars)
+  if (o.ngrains < 1) throw Abort("Properties.Grain.num_grains must be positive for a crystal-plasticity run");
+  const std::vector<double> quats = load_numbers(o.ori_file, 4L * o.ngrains, "orientation");
+  const long ne_coarse = (long)o.nxyz[0] * o.nxyz[1] * o.nxyz[2];
+  const std::vector<double> gmap = load_numbers(o.grain_map, ne_coarse, "grain map");
+  // ---- mesh: MakeCartesian3D + UniformRefinement (children inherit the parent's grain attribute) ----
+  const int f = 1 << (o.ser_ref_levels + o.par_ref_levels);
+  const int nx = o.nxyz[0] * f, ny = o.nxyz[1] * f, nz = o.nxyz[2] * f;
+  std::vector<int> grains((size_t)nx * ny * nz);
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) {
+        const long parent = ((long)(k / f) * o.nxyz[1] + (j / f)) * o.nxyz[0] + (i / f);
+        const int g = (int)gmap[parent];
+        if (g < 1 || g > o.ngrains) throw Abort("grain map entry out of range 1..num_grains");
+        grains[((size_t)k * ny + j) * nx + i] = g;
+      }
+  std::printf("mesh: %d x %d x %d hexes, %d grains\n", nx, ny, nz, o.ngrains);
+  // ---- time steps ----
+  if (o.dt_cust) o.cust_dt = load_numbers(o.dt_file, o.nsteps, "custom dt");
+  else if (o.dt_auto) o.nsteps = (int)std::ceil(o.t_final / o.dt_min);
+  else o.nsteps = (int)std::ceil(o.t_final / o.dt);
+  if (check_only) {  // parse + read inputs only (no GPU): used by the CPU test-suite
+    std::printf("check: xtal %d slip %d assembly %d integ %d nl_solver %d nprops %d nstate %d ngrains %d temp %g\n", (int)o.xtal_type,
+                (int)o.slip_type, (int)o.assembly, (int)o.integ_type, (int)o.nl_solver, o.nProps, o.numStateVars, o.ngrains, o.temp_k);
+    std::printf("check: nr %g %g %d krylov %g %g %d nsteps %d auto %d cust %d dt %g dt_min %g dt_scale %g t_final %g\n", o.newton_rel_tol,
+                o.newton_abs_tol, o.newton_iter, o.krylov_rel_tol, o.krylov_abs_tol, o.krylov_iter, o.nsteps, (int)o.dt_auto,
+                (int)o.dt_cust, o.dt, o.dt_min, o.dt_scale, o.t_final);
+    for (const BCSet& b : o.bcs) {
+      std::printf("check: bc step %d ids", b.step);
+      for (int v : b.ids) std::printf(" %d", v);
+      std::printf(" comps");
+      for (int v : b.comps) std::printf(" %d", v);
+      std::printf(" vals");
+      for (double v : b.vals) std::printf(" %g", v);
+      std::printf(" vgrad");
+      for (double v : b.vgrad) std::printf(" %g", v);
+      std::printf("\n");
+    }
+    long gsum = 0;
+    for (int g : grains) gsum += g;
+    std::printf("check: grain checksum %ld files %s %s %s %s\n", gsum, o.avg_stress_fname.c_str(), o.avg_pl_work_fname.c_str(),
+                o.avg_def_grad_fname.c_str(), o.avg_dp_tensor_fname.c_str());
+    return 0;
+  }
+  // ---- the simulation object ----
+  exahost_config c;
+  std::memset(&c, 0, sizeof(c));
+  c.nx = nx; c.ny = ny; c.nz_local = nz; c.z0 = 0; c.nz_total = nz;
+  for (int i = 0; i < 3; ++i) c.length[i] = o.mxyz[i];
+  c.xtal = (int)o.xtal_type; c.slip = (int)o.slip_type;
+  c.nprops = o.nProps; c.props = props.data(); c.temp_k = o.temp_k;
+  c.grain_ids = grains.data(); c.quats = quats.data(); c.ngrains = o.ngrains;
+  c.assembly = o.assembly == Assembly::EA ? EXAB200_EA : EXAB200_PA;
+  c.integ = (int)o.integ_type; c.nl_solver = (int)o.nl_solver;
+  c.newton_rel_tol = o.newton_rel_tol; c.newton_abs_tol = o.newton_abs_tol; c.newton_iter = o.newton_iter;
+  c.krylov_rel_tol = o.krylov_rel_tol; c.krylov_abs_tol = o.krylov_abs_tol; c.krylov_iter = o.krylov_iter;
+  c.true_jacobi = 0;
+  c.rank = 0; c.nranks = 1; c.device = 0; c.nccl_id = nullptr; c.verbose = 0;
+  exahost_sim* sim = nullptr;
+  if (exahost_create(&c, &sim)) throw Abort(exahost_last_error());
+  // ---- time loop (src/mechanics_driver.cpp:837-967) ----
+  double t = 0.0, ctl[6] = {o.dt, 0.0, o.dt_min, o.dt_scale, o.t_final, 0.0};
+  long newton_total = 0, pcg_total = 0;
+  const auto w0 = std::chrono::steady_clock::now();
+  for (int ti = 1; ti <= o.nsteps; ++ti) {
+    int changed = 0;
+    for (const BCSet& b : o.bcs)
+      if (b.step == ti) {
+        if (ti > 1) std::printf("Changing boundary conditions this step: %d\n", ti);
+        apply_bcs(sim, b, nx, ny, nz);
+        changed = 1;
+      }
+    double out[16];
+    bool last_step;
+    if (o.dt_auto) {
+      if (exahost_step_auto(sim, ctl, changed, nullptr, nullptr, out)) throw Abort(exahost_last_error());
+      t = ctl[1];
+      last_step = ctl[5] != 0.0;
+      std::ofstream file(o.dt_file, std::ios_base::app);
+      file.precision(12);
+      file << out[14] << std::endl;
+    } else {
+      const double dt_real = o.dt_cust ? o.cust_dt[ti - 1] : std::min(o.dt, o.t_final - t);
+      t += dt_real;
+      last_step = !o.dt_cust && std::fabs(t - o.t_final) <= std::fabs(1e-3 * dt_real);
+      if (exahost_step(sim, dt_real, changed, nullptr, nullptr, out)) throw Abort(exahost_last_error());
+    }
+    newton_total += (long)out[0];
+    pcg_total += (long)out[1];
+    {
+      std::ofstream file(o.avg_stress_fname, std::ios_base::app);
+      print_vector(file, &out[6], 6, 6);
+    }
+    if (o.additional_avgs) {
+      double ex[16];
+      if (exahost_extra_avgs(sim, ex)) throw Abort(exahost_last_error());
+      { std::ofstream file(o.avg_pl_work_fname, std::ios_base::app); file << ex[0] << std::endl; }
+      { std::ofstream file(o.avg_def_grad_fname, std::ios_base::app); print_vector(file, &ex[1], 9, 9); }
+      { std::ofstream file(o.avg_dp_tensor_fname, std::ios_base::app); print_vector(file, &ex[10], 6, 6); }
+    }
+    if (last_step || (ti % o.vis_steps) == 0)
+      std::printf("step %d, t = %g, newton %d, pcg %d, <sigma_zz> = %g\n", ti, t, (int)out[0], (int)out[1], out[8]);
+    if (last_step) break;
+  }
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+  std::printf("solve time %.3f s: %ld Newton iterations (%.3f Newton-steps/s), %ld PCG iterations, %ld kernel launches\n", wall,
+              newton_total, newton_total / wall, pcg_total, exahost_counter(sim, 0));
+  exahost_destroy(sim);
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::string opt = "options.toml";
+  bool check_only = false;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if ((a == "-opt" || a == "--option") && i + 1 < argc) opt = argv[++i];
+    else if (a == "--check") check_only = true;
+    else if (a == "-h" || a == "--help") { std::printf("usage: mechanics -opt <options.toml> [--check]\n"); return 0; }
+  }
+  try {
+    return run(opt, check_only);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "\nMFEM abort: %s\n", e.what());  // the reference aborts the job with this kind of message
+    return 1;
+  }
+}
