@@ -50,6 +50,12 @@ struct exab200_ctx {
   const double* xend_jac = nullptr;
   int variant_jx = 26, ctas_jx = 6;  // variant_jx < 0 disables the JX path
   int l2_hint = 1;                   // operand stream of the gradient apply marked L2 evict_first
+  // compact tangent records (EXAB200_TANGENT_COMPACT): written by model_setup, streamed by k_grad_mult_pa_c
+  int tangent_fmt = 0;
+  double* d_tan = nullptr;  // ctx-owned packed records, 32 doubles per point
+  CUtensorMap tmap;
+  bool tmap_valid = false;
+  int variant_c = 30, ctas_c = 6;
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
@@ -114,6 +120,58 @@ static int launch_grad_mult_jx(exab200_ctx* c, const double* x, double* y, ElemI
     case 28: return launch_gmw<1, 3, LVEC, ESS, true>(c, x, y, io, st, dot);
     case 29: return launch_gmw<3, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
     default: return launch_gmw<2, 2, LVEC, ESS, true>(c, x, y, io, st, dot);
+  }
+}
+// CUtensorMap over the packed tangent records [npts][32 doubles]; boxes of 32 rows x 16
+// doubles, 128-byte swizzle.  cuTensorMapEncodeTiled is a driver entry point: resolved at run time, no -lcuda.
+static int encode_tangent_map(exab200_ctx* c) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {32, (cuuint64_t)c->cfg.nelems * 8};
+  const cuuint64_t strides[1] = {32 * sizeof(double)};
+  const cuuint32_t box[2] = {16, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, c->d_tan, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  c->tmap_valid = true;
+  return 0;
+}
+template <int NW, int STAGES, bool ESS>
+static int launch_gmc(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
+  constexpr int smem = NW * STAGES * kWarpStageBytesC + NW * STAGES * 8 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_grad_mult_pa_c<NW, STAGES, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long nwt = (c->cfg.nelems + 3) / 4;
+  long grid = (long)c->sm_count * c->ctas_c;
+  if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
+  k_grad_mult_pa_c<NW, STAGES, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->tmap, x, y, io, c->cfg.nelems, c->grad_dt, dot,
+                                                                           c->d_xend);
+  POST_LAUNCH(c);
+  return 0;
+}
+template <bool ESS>
+static int launch_grad_mult_compact(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
+  switch (c->variant_c) {
+    case 31: return launch_gmc<2, 3, ESS>(c, x, y, io, st, dot);
+    case 32: return launch_gmc<4, 2, ESS>(c, x, y, io, st, dot);
+    case 33: return launch_gmc<1, 2, ESS>(c, x, y, io, st, dot);
+    case 34: return launch_gmc<2, 4, ESS>(c, x, y, io, st, dot);
+    case 35: return launch_gmc<1, 3, ESS>(c, x, y, io, st, dot);
+    default: return launch_gmc<2, 2, ESS>(c, x, y, io, st, dot);
   }
 }
 template <int MODE, bool ESS>
@@ -183,7 +241,8 @@ static int launch_k1(exab200_ctx* c, double dt, const double* d_jac, const doubl
   const unsigned nb = eblocks(c->cfg.nelems, kJS);
   k_model_setup<NSLIP, KIN, MODE, MINB><<<nb, kJS, kK1SmemBytes, st>>>(c->mat, dt, d_jac, d_vel,
                                                                          MODE == LVEC ? c->d_e2n : nullptr, c->cfg.nnodes, s0, h0, s1,
-                                                                         h1, mg, c->cfg.nelems, 1, c->d_fail);
+                                                                         h1, c->tangent_fmt ? c->d_tan : mg, c->cfg.nelems,
+                                                                         c->tangent_fmt ? mat::kTangentCompact : 1, c->d_fail);
   POST_LAUNCH(c);
   return 0;
 }
@@ -270,6 +329,7 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_fail);
   cudaFree(c->d_ea);
   cudaFree(c->d_xend);
+  cudaFree(c->d_tan);
   delete c;
 }
 
@@ -280,11 +340,26 @@ int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
   const int v = variant % 100;
   if (variant >= 100) c->k1_min_blocks = variant / 100;  // e.g. 210 -> K1 with 2 blocks/SM, K2 variant 10
   if (v >= 20 && v <= 29) { c->variant_jx = v; c->ctas_jx = ctas_per_sm; return 0; }
+  if (v >= 30 && v <= 35) { c->variant_c = v; c->ctas_c = ctas_per_sm; return 0; }
   if (v == 99) { c->variant_jx = -1; return 0; }
   if (v == 98 || v == 97) { c->l2_hint = (v == 98); return 0; }  // 98 / 97: L2 evict_first hint on / off  // stream J from HBM (the E-vector entry points always do)
   if (v > 15) return fail("bad tuning");
   c->ctas_per_sm = ctas_per_sm;
   c->variant = v;
+  return 0;
+}
+
+int exab200_set_tangent_format(exab200_ctx* c, int fmt) {
+  if (!c) return fail("null ctx");
+  if (fmt != EXAB200_TANGENT_VOIGT36 && fmt != EXAB200_TANGENT_COMPACT) return fail("unknown tangent format");
+  if (fmt == EXAB200_TANGENT_COMPACT) {
+    if (c->cfg.assembly != EXAB200_PA) return fail("compact tangent records are for partial assembly");
+    if (c->mat.Kvd != 0.0) return fail("compact tangent records are defined for cubic crystals only");
+    if (!c->d_e2n) return fail("compact tangent records need the L-vector connectivity");
+  }
+  if (fmt == EXAB200_TANGENT_COMPACT && !c->d_tan) CK(cudaMalloc(&c->d_tan, sizeof(double) * 32 * 8 * c->cfg.nelems));
+  c->tangent_fmt = fmt;
+  c->tmap_valid = false;
   return 0;
 }
 
@@ -367,6 +442,7 @@ int exab200_residual(exab200_ctx* c, const double* d_jac, const double* d_stress
 int exab200_ea_assemble(exab200_ctx* c, double dt, const double* d_matgrad, const double* d_jac, double* d_emat,
                         void* stream) {
   if (!c) return fail("null ctx");
+  if (c->tangent_fmt) return fail("element assembly reads the reference's 36-entry tangent layout (tangent format 0)");
   const unsigned nb = eblocks(c->cfg.nelems, 128);
   if (c->cfg.integ == EXAB200_INTEG_BBAR)
     k_assemble_ea<true><<<nb, 128, 0, (cudaStream_t)stream>>>(d_matgrad, d_jac, d_emat, c->cfg.nelems, dt);
@@ -379,6 +455,10 @@ int exab200_ea_assemble(exab200_ctx* c, double dt, const double* d_matgrad, cons
 int exab200_grad_setup(exab200_ctx* c, double dt, const double* d_matgrad, const double* d_jac, void* stream) {
   if (!c) return fail("null ctx");
   c->grad_dt = dt;
+  if (c->tangent_fmt && !c->tmap_valid) {
+    const int rc = encode_tangent_map(c);
+    if (rc) return rc;
+  }
   c->d_matgrad = d_matgrad;
   c->d_jac = d_jac;
   if (c->cfg.assembly == EXAB200_EA) {
@@ -390,6 +470,7 @@ int exab200_grad_setup(exab200_ctx* c, double dt, const double* d_matgrad, const
 
 int exab200_grad_mult_evec(exab200_ctx* c, const double* d_x_E, double* d_y_E, void* stream) {
   if (!c || !c->d_matgrad) return fail("grad_setup has not been called");
+  if (c->tangent_fmt) return fail("E-vector entry points read the reference's 36-entry tangent layout (tangent format 0)");
   ElemIO io{nullptr, nullptr, 0};
   if (c->cfg.assembly == EXAB200_EA) return exab200_ea_mult_evec(c, c->d_ea, d_x_E, d_y_E, stream);
   return launch_grad_mult_pa<EVEC, false>(c, d_x_E, d_y_E, io, (cudaStream_t)stream);
@@ -407,6 +488,12 @@ int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int
     k_ea_mult<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_x_L, d_y_L, io, c->cfg.nelems, d_dot_accum);
     POST_LAUNCH(c);
     return 0;
+  }
+  if (c->tangent_fmt) {
+    if (!(c->d_xend && c->xend_jac == c->d_jac))
+      return fail("compact tangent records need the Jacobian array written by the last exab200_setup_jacobians call");
+    if (ess) return launch_grad_mult_compact<true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+    return launch_grad_mult_compact<false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
   }
   if (c->variant_jx >= 0 && c->d_xend && c->xend_jac == c->d_jac) {
     if (ess) return launch_grad_mult_jx<true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
@@ -430,6 +517,7 @@ int exab200_ea_mult_evec(exab200_ctx* c, const double* d_emat, const double* d_x
 
 int exab200_grad_diag_evec(exab200_ctx* c, double* d_diag_E, void* stream) {
   if (!c || !c->d_matgrad) return fail("grad_setup has not been called");
+  if (c->tangent_fmt) return fail("E-vector entry points read the reference's 36-entry tangent layout (tangent format 0)");
   ElemIO io{nullptr, nullptr, 0};
   cudaStream_t st = (cudaStream_t)stream;
   if (c->cfg.assembly == EXAB200_EA)
@@ -448,6 +536,8 @@ int exab200_grad_diag(exab200_ctx* c, double* d_diag_L, void* stream) {
   ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
   if (c->cfg.assembly == EXAB200_EA)
     k_ea_diag<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_L, io, c->cfg.nelems);
+  else if (c->tangent_fmt)
+    k_grad_diag<LVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_tan, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
   else
     k_grad_diag<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
   POST_LAUNCH(c);

@@ -125,6 +125,17 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gm
       : "memory");
 }
 
+// 2-D tiled tensor copy global -> shared (TMA with a CUtensorMap descriptor, UTMALDG in SASS), completion counted
+// on an mbarrier; c0 = innermost coordinate (elements), c1 = row.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tensor_map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }

@@ -1060,6 +1060,8 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
     ec.nelems = s->nelems; ec.nnodes = s->nnodes; ec.e2n = e2n.data(); ec.assembly = cfg->assembly; ec.integ = cfg->integ;
     ec.device = cfg->device;
     XCK(exab200_create(&ec, &s->ctx));
+    // fused PA path on cubic crystals: K1 hands K2 the compact tangent record (11 % fewer operand bytes)
+    if (cfg->assembly == EXAB200_PA && cfg->xtal != EXAB200_HCP) XCK(exab200_set_tangent_format(s->ctx, EXAB200_TANGENT_COMPACT));
     const int nsv = exab200_num_state_vars(s->ctx);
     const long npts = s->nelems * 8, n = 3 * s->nnodes;
     s->stress0.SetSize(npts * 6); s->stress1.SetSize(npts * 6);
@@ -1356,7 +1358,11 @@ int exahost_kernel_time(exahost_sim* s, int which, double* total_ms, long* count
   if (reset) { t.total_ms = 0.0; t.count = 0; }
   return 0;
 }
-int exahost_set_tuning(exahost_sim* s, int ctas_per_sm, int variant) { return exab200_set_tuning(s->ctx, ctas_per_sm, variant); }
+int exahost_set_tuning(exahost_sim* s, int ctas_per_sm, int variant) {
+  // 95 / 96: reference 36-entry tangent layout / compact records (only meaningful before the first step)
+  if (variant == 95 || variant == 96) return exab200_set_tangent_format(s->ctx, variant == 96 ? EXAB200_TANGENT_COMPACT : EXAB200_TANGENT_VOIGT36);
+  return exab200_set_tuning(s->ctx, ctas_per_sm, variant);
+}
 
 // NVLink peer-memory collectives: every rank publishes the CUDA-IPC handle of its mailbox, the caller gathers
 // the handles of all ranks (torch.distributed) and hands them back.

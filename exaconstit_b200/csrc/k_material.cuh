@@ -21,7 +21,7 @@ namespace exab {
 // K1 kernel.  MODE as in k_operator.cuh (LVEC: vel is an L-vector gathered through e2n; EVEC:
 // vel is the E-vector the reference's ModelSetup receives).  Layouts: QFs (vdim,q,e),
 // jac (3,3,q,e), matgrad[(pt)*36 + j*6 + i] = d sigma_i / d eps_j (after the reference's transpose,
-// src/mechanics_ecmech.cpp:159-169; transpose=0 reproduces the EA-on-device quirk, :155).
+// src/mechanics_ecmech.cpp:159-169; layout 0 reproduces the EA-on-device quirk, :155; layout 2 = compact record).
 // The material description is a kernel parameter: its tables are constant-bank operands.
 // The 8x8 Jacobian of each thread lives in shared memory, entry k of thread t at smem[k * kJS + t]
 // (conflict-free, and off the local-memory / L2 path).
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant
                                                            long nnodes, const double* __restrict__ stress0,
                                                            const double* __restrict__ hist0, double* __restrict__ stress1,
                                                            double* __restrict__ hist1, double* __restrict__ matgrad,
-                                                           long nelems, int transpose, int* __restrict__ fail_count) {
+                                                           long nelems, int layout, int* __restrict__ fail_count) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 7;
   const long e = gt >> 3;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant
   }
   extern __shared__ double smJ[];
   const int nf = mat::update_point<NSLIP, KIN, kJS>(m, dt, L, hist0 + p * nsv, stress0 + p * 6, hist1 + p * nsv,
-                                                    stress1 + p * 6, matgrad + p * 36, transpose, smJ + threadIdx.x);
+                                                    stress1 + p * 6, matgrad + p * (layout == mat::kTangentCompact ? 32 : 36), layout, smJ + threadIdx.x);
   if (nf < 0) atomicAdd(fail_count, 1);
 }
 

@@ -2,7 +2,10 @@
 // tensor algebra).  Reference behaviour each kernel replaces is cited at its definition
 // (paths relative to the ExaConstit source tree).
 #pragma once
+#include <cuda.h>
+
 #include "exab200_common.cuh"
+#include "material_point.hpp"
 
 namespace exab {
 
@@ -379,6 +382,163 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// K2, compact-tangent variant (the default of the fused L-vector PA path for cubic crystals).  The operand is the
+// 32-double record K1 writes in layout kTangentCompact (mat::compact_apply: 25 + 6 + 1 values instead of 36), densely
+// packed at 256 B per point in a context-owned array, so 11 % fewer bytes leave HBM; J is rebuilt from the end coordinates as
+// in the JX kernels.  Each warp stage is two 32-row x 128-B boxes fetched by TWO tiled TMA copies
+// (cp.async.bulk.tensor.2d, CUtensorMap over [npts][32 doubles]) with the 128-byte hardware
+// swizzle: row r's 16-byte chunk c lands at chunk (c ^ (r & 7)), which makes the per-lane LDS.128 stream (lane =
+// row) bank-conflict free without padding or per-point copies.
+// ------------------------------------------------------------------------------------------
+constexpr int kBoxBytes = 32 * 128;               // 32 points x 16 doubles
+constexpr int kWarpStageBytesC = 2 * kBoxBytes;   // 8192
+
+template <int NW, int STAGES, bool ESS>
+__global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_c(const __grid_constant__ CUtensorMap tmap,
+                                                            const double* __restrict__ x, double* __restrict__ y,
+                                                            ElemIO io, long nelems, double dt,
+                                                            double* __restrict__ dot_accum,
+                                                            const double* __restrict__ xend) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
+  const int lane = l32 & 7;  // node / quadrature point
+  const int el = l32 >> 3;   // element slot in the warp's sub-tile
+  // the swizzle pattern is a function of the shared-memory address: 1024-byte aligned stages
+  unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* ring = base + (size_t)w * STAGES * kWarpStageBytesC;
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)NW * STAGES * kWarpStageBytesC) + w * STAGES;
+  const long nwt = (nelems + 3) >> 2;  // warp tiles of 4 elements = 32 points
+  const long stride = (long)gridDim.x * NW;
+  const long wt0 = (long)blockIdx.x * NW + w;
+  const uint64_t pol = l2_policy_evict_first();
+
+  if (l32 == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  auto issue = [&](long wt, int s) {
+    if (l32 == 0) {
+      unsigned char* sc = ring + s * kWarpStageBytesC;
+      mbar_arrive_expect_tx(&full[s], (uint32_t)kWarpStageBytesC);  // out-of-range rows are zero-filled and counted
+      tma_load_2d(sc, &tmap, 0, (int)(wt << 5), &full[s], pol);
+      tma_load_2d(sc + kBoxBytes, &tmap, 16, (int)(wt << 5), &full[s], pol);
+    }
+  };
+  {
+    long t = wt0;
+    for (int s = 0; s < STAGES; ++s, t += stride)
+      if (t < nwt) issue(t, s);
+  }
+
+  auto load_nid = [&](long wt) -> int {
+    const long e = (wt << 2) + el;
+    if (wt >= nwt || e >= nelems) return -1;
+    return io.e2n[e * 8 + lex_to_native(lane)];
+  };
+  auto load_x = [&](int nid, unsigned& msk, double& x0, double& x1, double& x2, double& c0, double& c1, double& c2) {
+    msk = 0; x0 = x1 = x2 = 0.0; c0 = c1 = c2 = 0.0;
+    if (nid < 0) return;
+    if (ESS) msk = io.essmask[nid];
+    x0 = x[nid]; x1 = x[io.nnodes + nid]; x2 = x[2 * io.nnodes + nid];
+    c0 = xend[nid]; c1 = xend[io.nnodes + nid]; c2 = xend[2 * io.nnodes + nid];
+  };
+
+  int nid_c = load_nid(wt0), nid_n = load_nid(wt0 + stride);
+  unsigned msk_c; double xc0, xc1, xc2, cc0, cc1, cc2;
+  load_x(nid_c, msk_c, xc0, xc1, xc2, cc0, cc1, cc2);
+
+  // this lane's row of the two boxes and its swizzle key
+  const int row_off = l32 * 128, key = (l32 & 7) << 4;
+
+  int s = 0;
+  uint32_t phase = 0;
+  double xdoty = 0.0;
+  for (long wt = wt0; wt < nwt; wt += stride) {
+    const int nid_n2 = load_nid(wt + 2 * stride);
+    unsigned msk_n; double xn0, xn1, xn2, cn0, cn1, cn2;
+    load_x(nid_n, msk_n, xn0, xn1, xn2, cn0, cn1, cn2);
+
+    const double u0 = (msk_c & 1) ? 0.0 : xc0, u1 = (msk_c & 2) ? 0.0 : xc1, u2 = (msk_c & 4) ? 0.0 : xc2;
+    double d00, d01, d02, d10, d11, d12, d20, d21, d22;
+    nodal_to_qp_grad(u0, lane, d00, d01, d02);
+    nodal_to_qp_grad(u1, lane, d10, d11, d12);
+    nodal_to_qp_grad(u2, lane, d20, d21, d22);
+    double J[9];
+    nodal_to_qp_grad(cc0, lane, J[0], J[3], J[6]);
+    nodal_to_qp_grad(cc1, lane, J[1], J[4], J[7]);
+    nodal_to_qp_grad(cc2, lane, J[2], J[5], J[8]);
+
+    mbar_wait(&full[s], phase);
+
+    const bool active = nid_c >= 0;
+    double t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0, t20 = 0, t21 = 0, t22 = 0;
+    if (active) {
+      const unsigned char* sc = ring + s * kWarpStageBytesC + row_off;
+      double rec[32];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const double2 v = *reinterpret_cast<const double2*>(sc + (c >> 3) * kBoxBytes + (((c & 7) << 4) ^ key));
+        rec[2 * c] = v.x;
+        rec[2 * c + 1] = v.y;
+      }
+      double adj[9];
+      const double det = adjugate(J, adj);
+      const double c = dt * kWq / det;
+      const double g00 = d00 * adj[0] + d01 * adj[3] + d02 * adj[6];
+      const double g01 = d00 * adj[1] + d01 * adj[4] + d02 * adj[7];
+      const double g02 = d00 * adj[2] + d01 * adj[5] + d02 * adj[8];
+      const double g10 = d10 * adj[0] + d11 * adj[3] + d12 * adj[6];
+      const double g11 = d10 * adj[1] + d11 * adj[4] + d12 * adj[7];
+      const double g12 = d10 * adj[2] + d11 * adj[5] + d12 * adj[8];
+      const double g20 = d20 * adj[0] + d21 * adj[3] + d22 * adj[6];
+      const double g21 = d20 * adj[1] + d21 * adj[4] + d22 * adj[7];
+      const double g22 = d20 * adj[2] + d21 * adj[5] + d22 * adj[8];
+      const double eps[6] = {c * g00, c * g11, c * g22, c * (g12 + g21), c * (g02 + g20), c * (g01 + g10)};
+      double S[6];
+      mat::compact_apply(rec, eps, S);
+      t00 = adj[0] * S[0] + adj[1] * S[5] + adj[2] * S[4];
+      t01 = adj[0] * S[5] + adj[1] * S[1] + adj[2] * S[3];
+      t02 = adj[0] * S[4] + adj[1] * S[3] + adj[2] * S[2];
+      t10 = adj[3] * S[0] + adj[4] * S[5] + adj[5] * S[4];
+      t11 = adj[3] * S[5] + adj[4] * S[1] + adj[5] * S[3];
+      t12 = adj[3] * S[4] + adj[4] * S[3] + adj[5] * S[2];
+      t20 = adj[6] * S[0] + adj[7] * S[5] + adj[8] * S[4];
+      t21 = adj[6] * S[5] + adj[7] * S[1] + adj[8] * S[3];
+      t22 = adj[6] * S[4] + adj[7] * S[3] + adj[8] * S[2];
+    }
+    // this stage's shared memory is dead: refill it before the output butterflies
+    __syncwarp();
+    {
+      const long tnext = wt + (long)STAGES * stride;
+      if (tnext < nwt) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(tnext, s);
+      }
+    }
+    const double y0 = qp_grad_to_nodal(t00, t10, t20, lane);
+    const double y1 = qp_grad_to_nodal(t01, t11, t21, lane);
+    const double y2 = qp_grad_to_nodal(t02, t12, t22, lane);
+    if (active) {
+      xdoty += u0 * y0 + u1 * y1 + u2 * y2;
+      if (!(msk_c & 1)) red_add_f64(&y[nid_c], y0);
+      if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
+      if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], y2);
+    }
+    nid_c = nid_n; nid_n = nid_n2;
+    msk_c = msk_n; xc0 = xn0; xc1 = xn1; xc2 = xn2;
+    cc0 = cn0; cc1 = cn1; cc2 = cn2;
+    if (++s == STAGES) { s = 0; phase ^= 1; }
+  }
+  if (dot_accum) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) xdoty += __shfl_xor_sync(kFull, xdoty, m);
+    if (l32 == 0) red_add_f64(dot_accum, xdoty);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Residual action: y_{a,k} += sum_q W_q [adj(J) sigma](j,k) G(a,j,q)
 // Replaces ExaNLFIntegrator::AssemblePA (three passes, src/mechanics_integrators.cpp:160-314)
 // + AddMultPA (:518-557) [+ restriction^T and essential-dof zeroing of MultVec,
@@ -474,7 +634,7 @@ __global__ void __launch_bounds__(256) k_residual(const double* __restrict__ str
 // lane = quadrature point; the 24 per-point partials are summed over the element with a
 // reduce-scatter butterfly (12 + 6 + 3 doubles), leaving node `lane`'s 3 entries in each lane.
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool COMPACT = false>
 __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ matgrad, const double* __restrict__ jac,
                                                    double* __restrict__ diag, ElemIO io, long nelems, double dt) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -487,11 +647,18 @@ __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ ma
   if (active) {
     double J[9], adj[9], K[36];
     const double* Jq = jac + (e * 8 + lane) * 9;
-    const double* Kq = matgrad + (e * 8 + lane) * 36;
+    const double* Kq = matgrad + (e * 8 + lane) * (COMPACT ? 32 : 36);
 #pragma unroll
     for (int i = 0; i < 9; ++i) J[i] = Jq[i];
+    if (COMPACT) {
+      double rec[32];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) K[i] = Kq[i];
+      for (int i = 0; i < 32; ++i) rec[i] = Kq[i];
+      mat::compact_expand(rec, K);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) K[i] = Kq[i];
+    }
     const double det = adjugate(J, adj);
     const double c = dt * kWq / det;
     const int vg[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};

@@ -85,6 +85,42 @@ constexpr double gam_ratio_min = 1.0e-60, gam_ratio_ovf = 1.0e45;
 constexpr double e_scale = 5.0e-4, r_scale = 1.0e-2;
 constexpr double kGrowthMax = 64.0;  // largest multiplier tolerated by the unpivoted factorisation
 
+// Compact tangent record (32 doubles in the point's 36-double slot; cubic crystals): [0..24] the 5x5 deviatoric
+// operator dsd (row-major, per unit strain increment), [25] kvol = -dp/dlnV, [26..31] the deviatoric Cauchy stress s'.
+// It expands to the Voigt 6x6 (engineering-shear columns) as
+//   K = Bm dsd Tm' + (-s'_i + [i<3] kvol) for the three normal-strain columns,
+// Tm' (5x6): deviatoric 5-vector of a Voigt strain with halved shear entries, Bm (6x5): Voigt stress of a 5-vector.
+constexpr int kTangentCompact = 2;
+// S = K eps for a Voigt (engineering shear) strain-like vector eps, straight from the compact record
+EXAB_HD void compact_apply(const double* __restrict__ rec, const double* eps, double* S) {
+  const double v[5] = {sqr2i * (eps[0] - eps[1]), sqr6i * (2.0 * eps[2] - eps[0] - eps[1]), sqr2i * eps[5], sqr2i * eps[4],
+                       sqr2i * eps[3]};
+  double w[5];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    double t = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) t += rec[a * 5 + b] * v[b];
+    w[a] = t;
+  }
+  const double tr = eps[0] + eps[1] + eps[2];
+  S[0] = sqr2i * w[0] - sqr6i * w[1] + (rec[25] - rec[26]) * tr;
+  S[1] = -sqr2i * w[0] - sqr6i * w[1] + (rec[25] - rec[27]) * tr;
+  S[2] = sqr2b3 * w[1] + (rec[25] - rec[28]) * tr;
+  S[3] = sqr2i * w[4] - rec[29] * tr;
+  S[4] = sqr2i * w[3] - rec[30] * tr;
+  S[5] = sqr2i * w[2] - rec[31] * tr;
+}
+// the Voigt 6x6 at K36[j*6+i] = d sigma_i / d eps_j from the compact record
+EXAB_HD void compact_expand(const double* __restrict__ rec, double* K36) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double e[6] = {0, 0, 0, 0, 0, 0};
+    e[j] = 1.0;
+    compact_apply(rec, e, &K36[j * 6]);
+  }
+}
+
 // packed index of the symmetric 5x5 accumulator, i <= j
 EXAB_HD constexpr int sidx(int i, int j) { return i * 5 - (i * (i - 1)) / 2 + (j - i); }
 EXAB_HD constexpr int sidx_sym(int i, int j) { return i <= j ? sidx(i, j) : sidx(j, i); }
@@ -776,15 +812,15 @@ EXAB_HD int solve_point(const MatDev& m, Point<NSLIP, KIN, JS>& P, double* x, do
 
 // ------------------------------------------------------------------------------------------
 // One material point.  L(i,t) = d v_i / d x_t; h0/s0: beginning-of-step history (m.nhist) and Cauchy stress
-// (Voigt 11,22,33,23,13,12); h1/s1: end-of-step; K: 36 tangent entries d sigma_i / d eps_j stored at
-// [j*6+i] when transpose != 0 (the layout after the reference's transpose, src/mechanics_ecmech.cpp:159-169),
-// else at [i*6+j]; J: this point's 8x8 scratch, J(i,j) at J[(i*8+j)*JS].
+// (Voigt 11,22,33,23,13,12); h1/s1: end-of-step; K: the tangent d sigma_i / d eps_j, `layout` 1: 36 entries at
+// [j*6+i] (the layout after the reference's transpose, src/mechanics_ecmech.cpp:159-169), 0: at [i*6+j], 2: the
+// compact record of kTangentCompact (cubic crystals only); J: this point's 8x8 scratch, J(i,j) at J[(i*8+j)*JS].
 // Returns the number of trial evaluations of the local solve, negative when it failed.
 // ------------------------------------------------------------------------------------------
 template <int NSLIP, int KIN, int JS>
 EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const double* __restrict__ h0,
                          const double* __restrict__ s0, double* __restrict__ h1, double* __restrict__ s1,
-                         double* __restrict__ K, int transpose, double* J) {
+                         double* __restrict__ K, int layout, double* J) {
   const int nsv = NSLIP + iH_Gdot + 2;
   const int ind_int_eng = nsv - 1, ind_vols = nsv - 2;
   // ---- kernel_setup ----
@@ -945,6 +981,17 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
 #pragma unroll
       for (int i = 0; i < 5; ++i) dsd[i][c] = col[i] * idt;
     }
+    if (layout == kTangentCompact) {
+      // private format of the fused PA path: the 6x6 is K = Bm dsd Tm' + (-s' + [i<3] kvol) (x) (1,1,1,0,0,0)
+#pragma unroll
+      for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) K[a * 5 + b] = dsd[a][b];
+      K[25] = -dp_dlnV;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) K[26 + i] = s6[i];
+      return nfev_s;
+    }
     // 5x5 deviatoric operator -> 6x6 Voigt (engineering-shear columns): K6 = Bm dsd Tm with the sparse maps
     //   Tm (5x6): vecd = Tm eps6 ; Bm (6x5): svec = Bm vecd ; shear columns halved
     double Mt[5][6];
@@ -989,7 +1036,7 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
           v += -s6[i] + hexb[i];
           if (i < 3) v += -dp_dlnV;
         }
-        K[transpose ? (j * 6 + i) : (i * 6 + j)] = v;
+        K[layout ? (j * 6 + i) : (i * 6 + j)] = v;
       }
     }
   }

@@ -81,6 +81,16 @@ int exab200_model_setup(exab200_ctx* ctx, double dt, const double* d_jac, const 
 int exab200_model_setup_evec(exab200_ctx* ctx, double dt, const double* d_jac, const double* d_vel_E,
                              const double* d_stress0, const double* d_hist0, double* d_stress1,
                              double* d_hist1, double* d_matgrad, void* stream);
+/* Where exab200_model_setup puts the material tangent and what the L-vector gradient entry points read.  VOIGT36
+ * (default) is the reference's matGrad layout above, in the caller's d_matgrad.  COMPACT is a private record of the
+ * fused PA path for cubic crystals (5x5 deviatoric operator, -dp/dlnV, deviatoric stress: 32 doubles, expanding to
+ * exactly the same 6x6) kept densely packed in context-owned memory (256 B per point; d_matgrad is then neither
+ * written nor read) that the gradient apply streams with 11 % fewer bytes; with it the E-vector entry points and
+ * exab200_ea_assemble, which are defined on the reference layout, return an error, and exab200_grad_mult needs the
+ * Jacobian array of the last exab200_setup_jacobians call. */
+enum { EXAB200_TANGENT_VOIGT36 = 0, EXAB200_TANGENT_COMPACT = 1 };
+int exab200_set_tangent_format(exab200_ctx* ctx, int format);
+
 /* number of points whose local Newton solve failed in model_setup calls since the last query
  * (ExaCMech raises on failure; the shim turns >0 into MFEM_ABORT).  Synchronises the stream. */
 int exab200_failed_points(exab200_ctx* ctx, void* stream, int* out);
@@ -143,7 +153,9 @@ long exab200_launch_count(const exab200_ctx* ctx);
  *     warp-private pipelines 10: 4 warps x 2 stages (default, 2 CTAs/SM), 11: 4x3, 12: 8x2, 13: 2x3, 14: 4x4, 15: 3x3;
  *   J rebuilt in registers from the end coordinates stored by exab200_setup_jacobians (L-vector entry points, used
  *     whenever the bound J array is the one that call wrote): 20: 4x2, 21: 4x3, 22: 8x2, 23: 4x4, 24: 2x3, 25: 3x3,
- *     26: 2x2 (default, 6 CTAs/SM), 27: 1x2, 28: 1x3, 29: 3x2;  99: disable the rebuilt-J path.
+ *     26: 2x2 (default, 6 CTAs/SM), 27: 1x2, 28: 1x3, 29: 3x2;  99: disable the rebuilt-J path;  98 / 97: L2
+ *     evict_first hint on the operand stream on / off;
+ *   compact tangent records (tiled, swizzled TMA): 30: 2x2 (default, 6 CTAs/SM), 31: 2x3, 32: 4x2, 33: 1x2, 34: 2x4, 35: 1x3.
  *   variant + 100*k additionally sets the material-update occupancy target to k CTAs/SM. */
 int exab200_set_tuning(exab200_ctx* ctx, int ctas_per_sm, int variant);
 

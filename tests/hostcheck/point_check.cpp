@@ -23,7 +23,7 @@ double adjugate(const double* J, double* adj) {
 
 template <int NSLIP, int KIN>
 long run(const MatDev& m, long ne, double dt, const double* jac, const double* G, const double* velE, const double* s0,
-         const double* h0, double* s1, double* h1, double* mg, long* nfev_sum) {
+         const double* h0, double* s1, double* h1, double* mg, long* nfev_sum, int layout) {
   const int nsv = m.nhist;
   long nfail = 0, nf = 0;
 #pragma omp parallel for reduction(+ : nfail, nf)
@@ -41,7 +41,7 @@ long run(const MatDev& m, long ne, double dt, const double* jac, const double* G
     for (int i = 0; i < 3; ++i)
       for (int t = 0; t < 3; ++t) L[i][t] = (d[i][0] * adj[t] + d[i][1] * adj[3 + t] + d[i][2] * adj[6 + t]) * idet;
     double J[64];
-    const int r = mat::update_point<NSLIP, KIN, 1>(m, dt, L, h0 + p * nsv, s0 + p * 6, h1 + p * nsv, s1 + p * 6, mg + p * 36, 1, J);
+    const int r = mat::update_point<NSLIP, KIN, 1>(m, dt, L, h0 + p * nsv, s0 + p * 6, h1 + p * nsv, s1 + p * 6, mg + p * 36, layout, J);
     if (r < 0) ++nfail;
     nf += r < 0 ? -r : r;
   }
@@ -54,24 +54,28 @@ extern "C" {
 // returns the number of failed points, or -1 on a bad material description
 long hostcheck_model_setup(int xtal, int kin, const double* props, int nprops, int force_pivot, int disable_powi, long ne,
                            double dt, const double* jac, const double* G, const double* velE, const double* s0,
-                           const double* h0, double* s1, double* h1, double* mg, long* nfev_sum) {
+                           const double* h0, double* s1, double* h1, double* mg, long* nfev_sum, int layout) {
   MatDev m;
   if (!build_material(m, xtal, kin, props, nprops).empty()) return -1;
   m.force_pivot = force_pivot;
   if (disable_powi) m.pl_n = 0;
   const bool km = kin == KIN_KMBALD;
   if (m.nslip == 12) {
-    if (km) return run<12, 1>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum);
-    return run<12, 0>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum);
+    if (km) return run<12, 1>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum, layout);
+    return run<12, 0>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum, layout);
   }
   if (!km) return -1;
-  return run<24, 1>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum);
+  return run<24, 1>(m, ne, dt, jac, G, velE, s0, h0, s1, h1, mg, nfev_sum, layout);
 }
 // solver path counters since the last call: 0 trial evaluations, 1 unused, 2 Jacobian re-evaluations (failed
 // solves only), 3 rejected trials, 4 pivoted-LU fallbacks in the Newton loop, 5 dogleg / Cauchy steps,
 // 6 pivoted-LU fallbacks in the tangent
 void hostcheck_stats(long* out8) {
   for (int i = 0; i < 8; ++i) { out8[i] = g_point_stats[i]; g_point_stats[i] = 0; }
+}
+// expands compact tangent records (layout 2) to the Voigt 6x6 layout, npts points, 36-double slots in and out
+void hostcheck_compact_expand(long npts, const double* rec, double* K36) {
+  for (long p = 0; p < npts; ++p) mat::compact_expand(rec + p * 36, K36 + p * 36);
 }
 int hostcheck_nhist(int xtal, int kin, const double* props, int nprops) {
   MatDev m;

@@ -216,3 +216,51 @@ def test_grad_mult_rebuilt_jacobians(n, variant, ctas):
     ctx.grad_mult(x, y_fb)
     assert hc.rel_err(y_fb.cpu().numpy(), cpu["y_grad"]) < OP_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("n,xtal,kin,variant,ctas", [(5, 0, 0, 30, 6), (6, 1, 0, 31, 4), (7, 0, 2, 32, 3), (9, 0, 0, 33, 8),
+                                                     (4, 1, 2, 34, 3), (8, 0, 1, 35, 6)])
+def test_compact_tangent_path(n, xtal, kin, variant, ctas):
+    """EXAB200_TANGENT_COMPACT: the material update writes the 32-double record and the gradient apply / diagonal read
+    it (tiled, swizzled TMA) -- same operator as the reference-layout path, which the tests above pin to the oracle."""
+    import torch
+    from exaconstit_b200 import capi
+    case = hc.make_case(n=n, seed=60 + n, ngrains=4, xtal=xtal, kin=kin)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    T = lambda a: torch.tensor(np.ascontiguousarray(a), **f64)
+    ne, nn, nsv, dt = case["ne"], case["nn"], case["nsv"], case["dt"]
+    res = {}
+    for fmt in (0, 1):
+        ctx = capi.Context(xtal, kin, case["props"], 298.0, ne, nn, case["e2n"], 0, 0)
+        ctx.set_essential_mask(case["essmask"])
+        ctx.set_tangent_format(fmt)
+        if fmt:
+            ctx.set_tuning(ctas, variant)
+        jac = torch.empty(ne * 72, **f64)
+        ctx.setup_jacobians(T(case["xbeg"]), T(case["vel"]), dt, jac)
+        s1, h1 = torch.empty(ne * 48, **f64), torch.empty(ne * 8 * nsv, **f64)
+        mg = torch.zeros(ne * 8 * 36, **f64)
+        ctx.model_setup(dt, jac, T(case["vel"]), T(case["stress0"]), T(case["hist0"]), s1, h1, mg)
+        assert ctx.failed_points() == 0
+        ctx.grad_setup(dt, mg, jac)
+        x = T(case["xvec"])
+        y, d = torch.empty(3 * nn, **f64), torch.empty(3 * nn, **f64)
+        ctx.grad_mult(x, y)
+        ctx.grad_diag(d)
+        acc = torch.zeros(1, **f64)
+        y2 = torch.zeros(3 * nn, **f64)
+        ctx.grad_mult_ex(x, y2, flags=2, dot_accum=acc)
+        yl = torch.empty(3 * nn, **f64)
+        ctx.grad_mult(x, yl, local_action=True)
+        torch.cuda.synchronize()
+        res[fmt] = dict(y=y.cpu().numpy(), d=d.cpu().numpy(), s1=s1.cpu().numpy(), h1=h1.cpu().numpy(), acc=acc.item(),
+                        y2=y2.cpu().numpy(), yl=yl.cpu().numpy())
+        if fmt:
+            with pytest.raises(capi.Exab200Error):
+                ctx.grad_mult_evec(torch.zeros(ne * 24, **f64), torch.zeros(ne * 24, **f64))
+        ctx.close()
+    a, b = res[0], res[1]
+    assert np.array_equal(a["s1"], b["s1"]) and np.array_equal(a["h1"], b["h1"])
+    for k in ("y", "d", "y2", "yl"):
+        assert hc.rel_err(b[k], a[k]) < 1e-12, k
+    assert abs(a["acc"] - b["acc"]) / abs(a["acc"]) < 1e-12

@@ -30,7 +30,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def run_host_point_update(case, force_pivot=0, disable_powi=0):
+def run_host_point_update(case, force_pivot=0, disable_powi=0, layout=1):
     from oracle import orc
     c = case
     xend = c["xbeg"] + c["dt"] * c["vel"]
@@ -45,7 +45,11 @@ def run_host_point_update(case, force_pivot=0, disable_powi=0):
     lib().hostcheck_stats(st)
     nfail = lib().hostcheck_model_setup(c["xtal"], c["kin"], _p(props), props.size, force_pivot, disable_powi, C.c_long(ne),
                                         C.c_double(c["dt"]), _p(jac), _p(G), _p(velE), _p(c["stress0"]), _p(c["hist0"]),
-                                        _p(s1), _p(h1), _p(mg), C.byref(nfev))
+                                        _p(s1), _p(h1), _p(mg), C.byref(nfev), layout)
+    if layout == 2:   # compact records -> Voigt 6x6 for the comparison
+        full = np.zeros_like(mg)
+        lib().hostcheck_compact_expand(C.c_long(ne * 8), _p(mg), _p(full))
+        mg = full
     lib().hostcheck_stats(st)
     names = ("trials", "unused", "rejac", "rejected", "pivot_loop", "dogleg", "pivot_tangent")
     return dict(nfail=nfail, stress1=s1, hist1=h1, matgrad=mg, nfev=nfev.value, stats=dict(zip(names, list(st))))
@@ -96,3 +100,15 @@ def test_point_update_dogleg_paths(xtal, kin, rate, dt):
     _check(case, out, cpu, tol=1e-10)
     st = out["stats"]
     assert st["rejected"] > 0 and st["dogleg"] > 0 and st["trials"] == out["nfev"]
+
+
+@pytest.mark.parametrize("xtal,kin", [(0, 0), (1, 0), (0, 1), (1, 2), (0, 2)])
+def test_compact_tangent_record_expands_to_the_voigt_tangent(xtal, kin):
+    """layout 2 (the private 32-double record the fused PA gradient apply streams: 5x5 deviatoric operator,
+    -dp/dlnV, deviatoric stress) expands to exactly the 6x6 the reference layout holds"""
+    case = hc.make_case(n=3, seed=21, ngrains=4, xtal=xtal, kin=kin)
+    cpu = hc.run_oracle_hot_path(case)
+    out = run_host_point_update(case, layout=2)
+    _check(case, out, cpu)
+    ref = run_host_point_update(case, layout=1)
+    assert hc.rel_err(out["matgrad"], ref["matgrad"]) < 1e-13

@@ -92,6 +92,22 @@ def main():
     print("JX vs streamed-J max rel diff:", float((y - y_jx).abs().max() / y.abs().max()))
     ctx.set_tuning(2, 10)
     ctx.set_tuning(6, 26)
+    # compact tangent records: needs a material update in that format first
+    ctx.set_tangent_format(1)
+    ctx.model_setup(dt, jac, vel, s0, hist0, s1, h1, mg)
+    ctx.grad_setup(dt, mg, jac)
+    for ctas, var in ([(6, 30), (5, 30), (4, 31), (3, 32), (8, 33), (11, 33), (3, 34), (8, 35)] if sweep else [(6, 30)]):
+        ctx.set_tuning(ctas, var)
+        t_med, t_min = timeit(lambda: ctx.grad_mult(x, y), iters=20, warm=3)
+        gbs = ne * 3264 / t_med / 1e6
+        res["grad_mult_compact_v%d_c%d" % (var, ctas)] = dict(ms=t_med, ms_min=t_min, GBps=gbs, frac=gbs / peak)
+    print("compact vs reference-layout max rel diff:", float((y - y_jx).abs().max() / y_jx.abs().max()))
+    ctx.set_tuning(6, 30)
+    t_med, _ = timeit(lambda: ctx.grad_diag(torch.empty_like(x)))
+    res["grad_diag_compact"] = dict(ms=t_med, GBps=ne * 3072 / t_med / 1e6)
+    ctx.set_tangent_format(0)
+    ctx.model_setup(dt, jac, vel, s0, hist0, s1, h1, mg)
+    ctx.grad_setup(dt, mg, jac)
     r = torch.empty_like(x)
     t_med, _ = timeit(lambda: ctx.residual(jac, s1, r))
     res["residual"] = dict(ms=t_med, GBps=ne * 1152 / t_med / 1e6)
