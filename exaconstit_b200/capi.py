@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libexab200.so")
+# EXAB200_LIBDIR: alternative build directory (tuning experiments only)
+LIB_PATH = os.path.join(os.environ.get("EXAB200_LIBDIR", os.path.join(_HERE, "lib")), "libexab200.so")
 
 FCC, BCC, HCP = 0, 1, 2
 POWERVOCE, POWERVOCENL, MTSDD = 0, 1, 2

@@ -39,6 +39,36 @@ __device__ __forceinline__ void nodal_to_qp_grad(double u, int lane, double& gx,
   gz = sz * (II - oII);
 }
 
+// Same transforms with the lane's three signs hoisted by the caller (persistent kernels: computed once per thread)
+struct LaneSigns { double sx, sy, sz; };
+__device__ __forceinline__ LaneSigns lane_signs(int lane) {
+  return LaneSigns{(lane & 1) ? 1.0 : -1.0, (lane & 2) ? 1.0 : -1.0, (lane & 4) ? 1.0 : -1.0};
+}
+__device__ __forceinline__ void nodal_to_qp_grad(double u, const LaneSigns& sg, double& gx, double& gy, double& gz) {
+  double o = shfl_xor_d(u, 1);
+  const double I = kAlpha * u + kBeta * o;
+  const double D = sg.sx * (u - o);
+  double oI = shfl_xor_d(I, 2), oD = shfl_xor_d(D, 2);
+  const double II = kAlpha * I + kBeta * oI;
+  const double DI = kAlpha * D + kBeta * oD;
+  const double ID = sg.sy * (I - oI);
+  const double oII = shfl_xor_d(II, 4), oDI = shfl_xor_d(DI, 4), oID = shfl_xor_d(ID, 4);
+  gx = kAlpha * DI + kBeta * oDI;
+  gy = kAlpha * ID + kBeta * oID;
+  gz = sg.sz * (II - oII);
+}
+__device__ __forceinline__ double qp_grad_to_nodal(double tx, double ty, double tz, const LaneSigns& sg) {
+  const double otx = shfl_xor_d(tx, 4), oty = shfl_xor_d(ty, 4), otz = shfl_xor_d(tz, 4);
+  const double DI = kAlpha * tx + kBeta * otx;
+  const double ID = kAlpha * ty + kBeta * oty;
+  const double II = sg.sz * (tz + otz);
+  const double oDI = shfl_xor_d(DI, 2), oID = shfl_xor_d(ID, 2), oII = shfl_xor_d(II, 2);
+  const double I = kAlpha * II + kBeta * oII + sg.sy * (ID + oID);
+  const double D = kAlpha * DI + kBeta * oDI;
+  const double oI = shfl_xor_d(I, 1), oD = shfl_xor_d(D, 1);
+  return kAlpha * I + kBeta * oI + sg.sx * (D + oD);
+}
+
 // Transpose of the above: per-quadrature-point (t_xi, t_eta, t_zeta) -> nodal value
 //   Y(a) = sum_q [ G(a,0,q) t_xi(q) + G(a,1,q) t_eta(q) + G(a,2,q) t_zeta(q) ].  8 double shuffles.
 __device__ __forceinline__ double qp_grad_to_nodal(double tx, double ty, double tz, int lane) {

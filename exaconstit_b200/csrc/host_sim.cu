@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(256) k_dot_partial(const double* __restrict__ 
                                                      long n_owned, double* __restrict__ partial) {
   // dot over the owned nodes of a byNODES L-vector: comps c in 0..2, nodes [0, n_owned)
   double s = 0.0;
-  const long total = 3 * n_owned;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long c = i / n_owned, n = i - c * n_owned;
-    s += a[c * nn + n] * b[c * nn + n];
+  for (int c = 0; c < 3; ++c) {
+    const long off = c * nn;
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < n_owned; n += (long)gridDim.x * blockDim.x)
+      s += a[off + n] * b[off + n];
   }
   __shared__ double red[8];
   for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
@@ -153,13 +153,16 @@ __global__ void __launch_bounds__(256) k_cg_step1(double* __restrict__ x, double
   const double alpha = *nom / *den;
   if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
   double s = 0.0;
-  const long total = 3 * nn;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    x[i] += alpha * d[i];
-    const double rn = r[i] - alpha * z[i];
-    r[i] = rn;
-    const long c = i / nn, n = i - c * nn;
-    if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+  // component by component: no 64-bit division in the streaming loop
+  for (int c = 0; c < 3; ++c) {
+    const long off = c * nn;
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
+      const long i = off + n;
+      x[i] += alpha * d[i];
+      const double rn = r[i] - alpha * z[i];
+      r[i] = rn;
+      if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+    }
   }
   __shared__ double red[8];
   for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
@@ -448,13 +451,16 @@ __global__ void __launch_bounds__(256) k_cg_step1_fused(double* __restrict__ x, 
   const double alpha = *nom / *den;
   if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
   double s = 0.0;
-  const long total = 3 * nn;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    x[i] += alpha * d[i];
-    const double rn = r[i] - alpha * z[i];
-    r[i] = rn;
-    const long c = i / nn, n = i - c * nn;
-    if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+  // component by component: no 64-bit division in the streaming loop
+  for (int c = 0; c < 3; ++c) {
+    const long off = c * nn;
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
+      const long i = off + n;
+      x[i] += alpha * d[i];
+      const double rn = r[i] - alpha * z[i];
+      r[i] = rn;
+      if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+    }
   }
   __shared__ double red[8];
   __shared__ bool last;
@@ -763,6 +769,14 @@ class NonlinearMechOperator : public Operator {
     return jacobian;
   }
   const unsigned char* ess_dev() const { return reinterpret_cast<const unsigned char*>(ess_mask_dev.d); }
+  // src/mechanics_operator.hpp:92-96
+  const unsigned char* GetEssTDofList() const { return ess_dev(); }   // per-node component mask instead of an index list
+  ExaModel* GetModel() const { return model; }
+  // src/mechanics_operator.cpp:393-427: F = I + grad_X u at the quadrature points of the REFERENCE mesh
+  void CalculateDeformationGradient(const Vector& x_ref, const Vector& x_cur, Vector& jac_ref, Vector& def_grad) const {
+    XCK(exab200_setup_jacobians(ctx, x_ref.Read(), nullptr, 0.0, jac_ref.Write(), stream));
+    XCK(exab200_grad_calc(ctx, jac_ref.Read(), x_cur.Read(), def_grad.Write(), stream));
+  }
 };
 
 void GradientOperator::Mult(const Vector& x, Vector& y) const {
@@ -1316,8 +1330,7 @@ int exahost_extra_avgs(exahost_sim* s, double* out16) {
     s->comm.AllReduceFetch(s->sums.d, nsv + 1, h);
     out16[0] = h[2];
     Vector jac_ref(s->nelems * 72), q9(npts * 9);
-    XCK(exab200_setup_jacobians(s->ctx, s->x_ref.Read(), nullptr, 0.0, jac_ref.Write(), s->stream));
-    XCK(exab200_grad_calc(s->ctx, jac_ref.Read(), s->x_beg.Read(), q9.Write(), s->stream));
+    s->oper->CalculateDeformationGradient(s->x_ref, s->x_beg, jac_ref, q9);
     XCK(exab200_vol_sum(s->ctx, s->oper->el_jac.Read(), q9.Read(), 9, s->sums.Write(), s->stream));
     s->comm.AllReduceFetch(s->sums.d, 10, h);
     for (int i = 0; i < 9; ++i) out16[1 + i] = h[i] / h[9];

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
   const uint64_t pol = l2_hint ? l2_policy_evict_first() : 0ull;
   constexpr int SB = JX ? kWarpStageBytesJX : kWarpStageBytes;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
+  const int w = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), l32 = threadIdx.x & 31;  // warp-uniform for the compiler
   const int lane = l32 & 7;  // node / quadrature point
   const int el = l32 >> 3;   // element slot in the warp's sub-tile
   unsigned char* ring = smem_raw + (size_t)w * STAGES * SB;
@@ -393,14 +393,17 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
 constexpr int kBoxBytes = 32 * 128;               // 32 points x 16 doubles
 constexpr int kWarpStageBytesC = 2 * kBoxBytes;   // 8192
 
+// register cap: 12 resident warps per SM (6 CTAs of 2 warps, 3 of 4, 12 of 1)
 template <int NW, int STAGES, bool ESS>
-__global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_c(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __grid_constant__ CUtensorMap tmap,
                                                             const double* __restrict__ x, double* __restrict__ y,
                                                             ElemIO io, long nelems, double dt,
                                                             double* __restrict__ dot_accum,
                                                             const double* __restrict__ xend) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int w = threadIdx.x >> 5, l32 = threadIdx.x & 31;
+  // warp index through a broadcast: tells the compiler it is warp-uniform (uniform loop bounds, no re-convergence
+  // barriers around the shuffles)
+  const int w = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), l32 = threadIdx.x & 31;
   const int lane = l32 & 7;  // node / quadrature point
   const int el = l32 >> 3;   // element slot in the warp's sub-tile
   // the swizzle pattern is a function of the shared-memory address: 1024-byte aligned stages
@@ -451,6 +454,7 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_c(const __grid_constan
 
   // this lane's row of the two boxes and its swizzle key
   const int row_off = l32 * 128, key = (l32 & 7) << 4;
+  const LaneSigns sg = lane_signs(lane);
 
   int s = 0;
   uint32_t phase = 0;
@@ -462,19 +466,22 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_c(const __grid_constan
 
     const double u0 = (msk_c & 1) ? 0.0 : xc0, u1 = (msk_c & 2) ? 0.0 : xc1, u2 = (msk_c & 4) ? 0.0 : xc2;
     double d00, d01, d02, d10, d11, d12, d20, d21, d22;
-    nodal_to_qp_grad(u0, lane, d00, d01, d02);
-    nodal_to_qp_grad(u1, lane, d10, d11, d12);
-    nodal_to_qp_grad(u2, lane, d20, d21, d22);
+    nodal_to_qp_grad(u0, sg, d00, d01, d02);
+    nodal_to_qp_grad(u1, sg, d10, d11, d12);
+    nodal_to_qp_grad(u2, sg, d20, d21, d22);
     double J[9];
-    nodal_to_qp_grad(cc0, lane, J[0], J[3], J[6]);
-    nodal_to_qp_grad(cc1, lane, J[1], J[4], J[7]);
-    nodal_to_qp_grad(cc2, lane, J[2], J[5], J[8]);
+    nodal_to_qp_grad(cc0, sg, J[0], J[3], J[6]);
+    nodal_to_qp_grad(cc1, sg, J[1], J[4], J[7]);
+    nodal_to_qp_grad(cc2, sg, J[2], J[5], J[8]);
 
     mbar_wait(&full[s], phase);
 
+    // No branch around the arithmetic: an inactive 8-lane group (only in the last, partial tile) works on
+    // zero-filled rows and zero coordinates; whatever it produces (inf/NaN from det = 0) stays inside the group
+    // and is never stored.  Uniform control flow keeps the shuffles free of re-convergence overhead.
     const bool active = nid_c >= 0;
-    double t00 = 0, t01 = 0, t02 = 0, t10 = 0, t11 = 0, t12 = 0, t20 = 0, t21 = 0, t22 = 0;
-    if (active) {
+    double t00, t01, t02, t10, t11, t12, t20, t21, t22;
+    {
       const unsigned char* sc = ring + s * kWarpStageBytesC + row_off;
       double rec[32];
 #pragma unroll
@@ -517,9 +524,9 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_c(const __grid_constan
         issue(tnext, s);
       }
     }
-    const double y0 = qp_grad_to_nodal(t00, t10, t20, lane);
-    const double y1 = qp_grad_to_nodal(t01, t11, t21, lane);
-    const double y2 = qp_grad_to_nodal(t02, t12, t22, lane);
+    const double y0 = qp_grad_to_nodal(t00, t10, t20, sg);
+    const double y1 = qp_grad_to_nodal(t01, t11, t21, sg);
+    const double y2 = qp_grad_to_nodal(t02, t12, t22, sg);
     if (active) {
       xdoty += u0 * y0 + u1 * y1 + u2 * y2;
       if (!(msk_c & 1)) red_add_f64(&y[nid_c], y0);

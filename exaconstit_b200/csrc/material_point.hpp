@@ -46,6 +46,15 @@ namespace exab { extern long g_point_stats[8]; }
 #define EXAB_STAT(k) ((void)0)
 #endif
 
+// unroll factor of the 12-system slip loops of the power-law path (tuning knob: full unrolling maximises ILP and
+// uses immediate constant operands, partial unrolling shrinks the hot loop's instruction footprint)
+#ifndef EXAB_SLIP_UNROLL
+#define EXAB_SLIP_UNROLL 12
+#endif
+#define EXAB_PRAGMA_(x) _Pragma(#x)
+#define EXAB_PRAGMA(x) EXAB_PRAGMA_(x)
+#define EXAB_UNROLL_SLIP EXAB_PRAGMA(unroll EXAB_SLIP_UNROLL)
+
 namespace exab {
 
 constexpr int kMaxSlip = 24;
@@ -525,7 +534,7 @@ struct Point {
       // power law, one resistance: tau/g for all systems, then |tau/g|^(1/m - 1) for all systems at once
       const double gi = 1.0 / g[0], xmi = m.xmi;
       double tt[NSLIP], pl[NSLIP];
-#pragma unroll
+EXAB_UNROLL_SLIP
       for (int a = 0; a < NSLIP; ++a) {
         double tau = 0.0;
 #pragma unroll
@@ -552,7 +561,7 @@ struct Point {
         }
       }
       const double gw_xmi_gi = gam_w * xmi * gi;
-#pragma unroll
+EXAB_UNROLL_SLIP
       for (int a = 0; a < NSLIP; ++a) {
         const double t = tt[a], at = fabs(t);
         double gd, dg;
@@ -575,7 +584,7 @@ struct Point {
         tt[a] = dg;
       }
       if (want_jac) {
-#pragma unroll
+EXAB_UNROLL_SLIP
         for (int a = 0; a < NSLIP; ++a) {
           const double dg = tt[a];
 #pragma unroll

@@ -8,7 +8,8 @@ import numpy as np
 from . import capi, voxel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libexahost.so")
+# EXAB200_LIBDIR: alternative build directory (tuning experiments only)
+LIB_PATH = os.path.join(os.environ.get("EXAB200_LIBDIR", os.path.join(_HERE, "lib")), "libexahost.so")
 
 
 class HostConfig(C.Structure):

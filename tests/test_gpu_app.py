@@ -44,6 +44,11 @@ def test_constant_strain_rate_ea_with_additional_averages(tmp_path):
     dp = np.loadtxt(os.path.join(str(tmp_path), "test_dp_tensor.txt"))
     assert F.shape == (n, 9) and plw.shape == (n,) and dp.shape == (n, 6)
     assert abs(F[-1, 8] - np.exp(1e-3 * g["custom_dt"][:n].sum())) < 1e-5     # constant true strain rate along z
+    # the reference's own additional-average goldens of this case (6 printed digits)
+    assert np.abs(F - g["voce_ea_cs_def_grad"][:n]).max() < 6e-6
+    gp, gd = g["voce_ea_cs_pl_work"][:n], g["voce_ea_cs_dp_tensor"][:n]
+    assert np.abs(plw - gp).max() / np.abs(gp).max() < 2e-4
+    assert np.abs(dp - gd).max() / np.abs(gd).max() < 2e-4
 
 
 def test_changing_mixed_bcs_fixed_time_steps(tmp_path):

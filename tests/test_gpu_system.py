@@ -20,7 +20,8 @@ def _gpu_run(name, nsteps, **kw):
     return hist, state, gold[:nsteps], inp, launches
 
 
-@pytest.mark.parametrize("name,nsteps", [("voce_pa", 12), ("voce_ea", 6), ("mtsdd_bcc", 8)])
+@pytest.mark.parametrize("name,nsteps", [("voce_pa", 12), ("voce_ea", 6), ("mtsdd_bcc", 8), ("voce_bcc", 6), ("voce_nl_full", 6),
+                                         ("mtsdd_full", 8)])
 def test_time_history_matches_oracle_and_golden(orc, name, nsteps):
     hist, state, gold, inp, launches = _gpu_run(name, nsteps)
     inp2 = dict(inp)
@@ -191,3 +192,33 @@ def test_config5_small_hcp_bbar_ea_nrls_cyclic(orc):
     s = np.array([h["avg_stress"] for h in hist])
     assert (np.abs(s - ref["stress"]) / np.abs(ref["stress"]).max()).max() < 1e-8
     assert [h["newton_iters"] for h in hist] == list(ref["iters"][:, 0])
+
+
+@pytest.mark.parametrize("n,xtal,kin,props_key,ngrains", [(32, 0, 0, "props_cp_voce", 100), (64, 1, 2, "props_cp_mts", 500)])
+def test_baseline_configs_at_full_size(n, xtal, kin, props_key, ngrains):
+    """BASELINE configs 2 (32^3, 100 grains, FCC Voce) and 3 (64^3, 500 grains, BCC KMBalD) at their full sizes, judged
+    through size-independent properties: Newton converges, no local solve fails, the free lateral faces leave the
+    averaged lateral stresses at zero (and the shear ones small), the loaded component follows the elastic slope in the first step and
+    bends over once the polycrystal yields, and the run is reproducible to round-off (red.add ordering only)."""
+    from exaconstit_b200 import host, voxel
+    g = refcases.goldens()
+    grains = voxel.voronoi_grains(n, n, n, ngrains, 1000 * n + ngrains)
+    quats = g["voce_quats"][:ngrains]
+    nr, kr = ((5e-5, 5e-10, 25), (1e-7, 1e-27, 1000)) if kin == 0 else ((1e-5, 1e-12, 25), (1e-7, 1e-27, 250))
+    dts = [0.005, 0.195, 0.2, 0.2]
+    runs = []
+    for _ in range(2):
+        sim = host.VoxelSim((n, n, n), (1.0, 1.0, 1.0), xtal, kin, g[props_key], 298.0, grains, quats, nr=nr, kr=kr)
+        hist = sim.run(dts, refcases.uniaxial_bcs())
+        sim.close()
+        runs.append(np.array([h["avg_stress"] for h in hist]))
+        assert all(h["converged"] for h in hist)
+    s = runs[0]
+    szz = s[:, 2]
+    assert np.all(szz > 0) and np.all(np.diff(szz) > 0)
+    assert np.abs(s[:, [0, 1]]).max() < 1e-5 * szz[-1]            # free lateral faces: no average lateral stress
+    assert np.abs(s[:, [3, 4, 5]]).max() < 3e-2 * szz[-1]         # polycrystal anisotropy leaves only small average shear
+    e_slope = szz[0] / 0.005
+    assert abs(szz[1] / 0.2 - e_slope) / e_slope < 0.02          # still elastic after 0.2 s
+    assert (szz[3] - szz[2]) / 0.2 < 0.8 * e_slope                # yielding: tangent below the elastic slope
+    assert np.abs(runs[0] - runs[1]).max() / szz[-1] < 1e-9
