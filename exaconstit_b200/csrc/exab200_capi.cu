@@ -56,6 +56,7 @@ struct exab200_ctx {
   CUtensorMap tmap;
   bool tmap_valid = false;
   int variant_c = 30, ctas_c = 6;
+  int variant_ea = 40, ctas_ea = 3;
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
@@ -172,6 +173,35 @@ static int launch_grad_mult_compact(exab200_ctx* c, const double* x, double* y, 
     case 34: return launch_gmc<2, 4, ESS>(c, x, y, io, st, dot);
     case 35: return launch_gmc<1, 3, ESS>(c, x, y, io, st, dot);
     default: return launch_gmc<2, 2, ESS>(c, x, y, io, st, dot);
+  }
+}
+template <int NW, int STAGES, bool ESS>
+static int launch_eap(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot, int ctas) {
+  constexpr int smem = NW * STAGES * kEaStageBytes + NW * STAGES * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_ea_mult_p<NW, STAGES, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long nwt = (c->cfg.nelems + 3) / 4;
+  long grid = (long)c->sm_count * ctas;
+  if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
+  k_ea_mult_p<NW, STAGES, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->d_ea, x, y, io, c->cfg.nelems, dot);
+  POST_LAUNCH(c);
+  return 0;
+}
+// pipelined EA apply {warps per CTA, stages}: 40: 2x2 (3 CTAs/SM, default), 41: 1x2 (6), 42: 1x3 (4), 43: 2x3 (2); 49: plain kernel
+template <bool ESS>
+static int launch_ea_mult(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
+  switch (c->variant_ea) {
+    case 41: return launch_eap<1, 2, ESS>(c, x, y, io, st, dot, c->ctas_ea);
+    case 42: return launch_eap<1, 3, ESS>(c, x, y, io, st, dot, c->ctas_ea);
+    case 43: return launch_eap<2, 3, ESS>(c, x, y, io, st, dot, c->ctas_ea);
+    case 49:
+      k_ea_mult<LVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, x, y, io, c->cfg.nelems, dot);
+      POST_LAUNCH(c);
+      return 0;
+    default: return launch_eap<2, 2, ESS>(c, x, y, io, st, dot, c->ctas_ea);
   }
 }
 template <int MODE, bool ESS>
@@ -341,6 +371,7 @@ int exab200_set_tuning(exab200_ctx* c, int ctas_per_sm, int variant) {
   if (variant >= 100) c->k1_min_blocks = variant / 100;  // e.g. 210 -> K1 with 2 blocks/SM, K2 variant 10
   if (v >= 20 && v <= 29) { c->variant_jx = v; c->ctas_jx = ctas_per_sm; return 0; }
   if (v >= 30 && v <= 35) { c->variant_c = v; c->ctas_c = ctas_per_sm; return 0; }
+  if (v >= 40 && v <= 49) { c->variant_ea = v; c->ctas_ea = ctas_per_sm; return 0; }
   if (v == 99) { c->variant_jx = -1; return 0; }
   if (v == 98 || v == 97) { c->l2_hint = (v == 98); return 0; }  // 98 / 97: L2 evict_first hint on / off  // stream J from HBM (the E-vector entry points always do)
   if (v > 15) return fail("bad tuning");
@@ -461,9 +492,15 @@ int exab200_grad_setup(exab200_ctx* c, double dt, const double* d_matgrad, const
   }
   c->d_matgrad = d_matgrad;
   c->d_jac = d_jac;
-  if (c->cfg.assembly == EXAB200_EA) {
+  if (c->cfg.assembly == EXAB200_EA) {  // context-owned element matrices, lane-interleaved private layout
     CK(cudaMemsetAsync(c->d_ea, 0, sizeof(double) * 576 * c->cfg.nelems, (cudaStream_t)stream));
-    return exab200_ea_assemble(c, dt, d_matgrad, d_jac, c->d_ea, stream);
+    const unsigned nb = eblocks(c->cfg.nelems, 128);
+    if (c->cfg.integ == EXAB200_INTEG_BBAR)
+      k_assemble_ea<true, true><<<nb, 128, 0, (cudaStream_t)stream>>>(d_matgrad, d_jac, c->d_ea, c->cfg.nelems, dt);
+    else
+      k_assemble_ea<false, true><<<nb, 128, 0, (cudaStream_t)stream>>>(d_matgrad, d_jac, c->d_ea, c->cfg.nelems, dt);
+    POST_LAUNCH(c);
+    return 0;
   }
   return 0;
 }
@@ -472,7 +509,11 @@ int exab200_grad_mult_evec(exab200_ctx* c, const double* d_x_E, double* d_y_E, v
   if (!c || !c->d_matgrad) return fail("grad_setup has not been called");
   if (c->tangent_fmt) return fail("E-vector entry points read the reference's 36-entry tangent layout (tangent format 0)");
   ElemIO io{nullptr, nullptr, 0};
-  if (c->cfg.assembly == EXAB200_EA) return exab200_ea_mult_evec(c, c->d_ea, d_x_E, d_y_E, stream);
+  if (c->cfg.assembly == EXAB200_EA) {
+    k_ea_mult<EVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, (cudaStream_t)stream>>>(c->d_ea, d_x_E, d_y_E, io, c->cfg.nelems, nullptr);
+    POST_LAUNCH(c);
+    return 0;
+  }
   return launch_grad_mult_pa<EVEC, false>(c, d_x_E, d_y_E, io, (cudaStream_t)stream);
 }
 
@@ -485,9 +526,8 @@ int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int
   const bool ess = c->have_ess && !local_action;
   ElemIO io{c->d_e2n, ess ? c->d_ess : nullptr, c->cfg.nnodes};
   if (c->cfg.assembly == EXAB200_EA) {
-    k_ea_mult<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_x_L, d_y_L, io, c->cfg.nelems, d_dot_accum);
-    POST_LAUNCH(c);
-    return 0;
+    if (ess) return launch_ea_mult<true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+    return launch_ea_mult<false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
   }
   if (c->tangent_fmt) {
     if (!(c->d_xend && c->xend_jac == c->d_jac))
@@ -521,7 +561,7 @@ int exab200_grad_diag_evec(exab200_ctx* c, double* d_diag_E, void* stream) {
   ElemIO io{nullptr, nullptr, 0};
   cudaStream_t st = (cudaStream_t)stream;
   if (c->cfg.assembly == EXAB200_EA)
-    k_ea_diag<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_E, io, c->cfg.nelems);
+    k_ea_diag<EVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_E, io, c->cfg.nelems);
   else
     k_grad_diag<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_E, io, c->cfg.nelems, c->grad_dt);
   POST_LAUNCH(c);
@@ -535,7 +575,7 @@ int exab200_grad_diag(exab200_ctx* c, double* d_diag_L, void* stream) {
   CK(cudaMemsetAsync(d_diag_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
   ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
   if (c->cfg.assembly == EXAB200_EA)
-    k_ea_diag<LVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_L, io, c->cfg.nelems);
+    k_ea_diag<LVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_L, io, c->cfg.nelems);
   else if (c->tangent_fmt)
     k_grad_diag<LVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_tan, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
   else

@@ -773,7 +773,11 @@ __global__ void __launch_bounds__(256) k_jacobians(const double* __restrict__ xb
 // lane = column node k; it loops the element's 8 points and keeps its 24x3 column block in
 // registers; rows/cols are in NATIVE node order like the reference.
 // ------------------------------------------------------------------------------------------
-template <bool BBAR>
+// PRIV selects the context-private storage of the L-vector EA path: the 72 entries lane k owns (its 3 columns) are
+// interleaved with the other lanes' in 16-byte chunks, value v = comp*24 + row_native at
+// ea[e*576 + ((v >> 1) * 8 + lane) * 2 + (v & 1)], so that every LDG/STG.128 of the 8 lanes of an element covers 128
+// contiguous bytes (the reference layout gives each lane a private 192-byte column: 32 sectors per warp request).
+template <bool BBAR, bool PRIV = false>
 __global__ void __launch_bounds__(128) k_assemble_ea(const double* __restrict__ matgrad, const double* __restrict__ jac,
                                                      double* __restrict__ ea, long nelems, double dt) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -872,7 +876,14 @@ __global__ void __launch_bounds__(128) k_assemble_ea(const double* __restrict__ 
     for (int l = 0; l < 8; ++l) {
       const int ln = lex_to_native(l);
 #pragma unroll
-      for (int I = 0; I < 3; ++I) col[ln + 8 * I] += acc[l][I][Kc];
+      for (int I = 0; I < 3; ++I) {
+        if (PRIV) {
+          const int v = Kc * 24 + ln + 8 * I;
+          ea[e * 576 + ((v >> 1) * 8 + lane) * 2 + (v & 1)] += acc[l][I][Kc];
+        } else {
+          col[ln + 8 * I] += acc[l][I][Kc];
+        }
+      }
     }
   }
 }
@@ -883,7 +894,7 @@ __global__ void __launch_bounds__(128) k_assemble_ea(const double* __restrict__ 
 // j = lane_native + 8*comp.  LVEC fuses restriction, restriction^T and essential-dof masking
 // (EANonlinearMechOperatorGradExt::TMult, :278-328).
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool PRIV = false>
 __global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, const double* __restrict__ x,
                                                  double* __restrict__ y, ElemIO io, long nelems,
                                                  double* __restrict__ dot_accum) {
@@ -920,11 +931,12 @@ __global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, 
   if (active) {
 #pragma unroll
   for (int cmp = 0; cmp < 3; ++cmp) {
-    const double2* col = reinterpret_cast<const double2*>(ea + e * 576 + (long)(an + 8 * cmp) * 24);
+    // reference layout: this lane's column is 192 contiguous bytes; private layout: chunk-interleaved over the lanes
+    const double2* col = reinterpret_cast<const double2*>(ea + e * 576 + (PRIV ? (long)(cmp * 12 * 8 + lane) * 2 : (long)(an + 8 * cmp) * 24));
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
-      const double2 m = col[i];
+      const double2 m = col[PRIV ? i * 8 : i];
       s0 += m.x * xe[2 * i];
       s1 += m.y * xe[2 * i + 1];
     }
@@ -946,8 +958,123 @@ __global__ void __launch_bounds__(256) k_ea_mult(const double* __restrict__ ea, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Element-matrix apply of the L-vector EA path, pipelined like K2: persistent CTAs, every warp owns a STAGES-deep ring
+// of 4-element sub-tiles (4 x 4608 B of the context-private, lane-interleaved element matrices: ONE bulk TMA copy per
+// stage since consecutive elements are contiguous), completion on the warp's own mbarriers, refill right after the
+// last shared-memory read.  In shared memory lane k's i-th 16-byte chunk sits at ((c*12 + i)*8 + k)*16, so the 8 lanes
+// of an element read 128 contiguous bytes per LDS.128: conflict-free.
+// ------------------------------------------------------------------------------------------
+constexpr int kEaElemBytes = 576 * 8;
+constexpr int kEaStageBytes = 4 * kEaElemBytes;  // 18432
+
+template <int NW, int STAGES, bool ESS>
+__global__ void __launch_bounds__(NW * 32) k_ea_mult_p(const double* __restrict__ ea, const double* __restrict__ x,
+                                                       double* __restrict__ y, ElemIO io, long nelems,
+                                                       double* __restrict__ dot_accum) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), l32 = threadIdx.x & 31;
+  const int lane = l32 & 7, el = l32 >> 3;
+  unsigned char* ring = smem_raw + (size_t)w * STAGES * kEaStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NW * STAGES * kEaStageBytes) + w * STAGES;
+  const long nwt = (nelems + 3) >> 2;
+  const long stride = (long)gridDim.x * NW;
+  const long wt0 = (long)blockIdx.x * NW + w;
+  const uint64_t pol = l2_policy_evict_first();
+  if (l32 == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](long wt, int s) {
+    if (l32 == 0) {
+      const long e0 = wt << 2;
+      const uint32_t bytes = (uint32_t)min(4L, nelems - e0) * kEaElemBytes;
+      mbar_arrive_expect_tx(&full[s], bytes);
+      bulk_g2s_hint(ring + s * kEaStageBytes, ea + e0 * 576, bytes, &full[s], pol);
+    }
+  };
+  {
+    long t = wt0;
+    for (int s = 0; s < STAGES; ++s, t += stride)
+      if (t < nwt) issue(t, s);
+  }
+  auto load_nid = [&](long wt) -> int {
+    const long e = (wt << 2) + el;
+    if (wt >= nwt || e >= nelems) return -1;
+    return io.e2n[e * 8 + lex_to_native(lane)];
+  };
+  auto load_x = [&](int nid, unsigned& msk, double& x0, double& x1, double& x2) {
+    msk = 0; x0 = x1 = x2 = 0.0;
+    if (nid < 0) return;
+    if (ESS) msk = io.essmask[nid];
+    x0 = x[nid]; x1 = x[io.nnodes + nid]; x2 = x[2 * io.nnodes + nid];
+  };
+  int nid_c = load_nid(wt0), nid_n = load_nid(wt0 + stride);
+  unsigned msk_c; double xc0, xc1, xc2;
+  load_x(nid_c, msk_c, xc0, xc1, xc2);
+  const int base = l32 & ~7;
+  int s = 0;
+  uint32_t phase = 0;
+  double xdoty = 0.0;
+  for (long wt = wt0; wt < nwt; wt += stride) {
+    const int nid_n2 = load_nid(wt + 2 * stride);
+    unsigned msk_n; double xn0, xn1, xn2;
+    load_x(nid_n, msk_n, xn0, xn1, xn2);
+    const double u0 = (msk_c & 1) ? 0.0 : xc0, u1 = (msk_c & 2) ? 0.0 : xc1, u2 = (msk_c & 4) ? 0.0 : xc2;
+    // all 24 element dofs to every lane: xe[a_native + 8*comp]
+    double xe[24];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int src = base + lex_to_native(a);  // lane holding native node a (lex_to_native is an involution)
+      xe[a] = __shfl_sync(kFull, u0, src);
+      xe[a + 8] = __shfl_sync(kFull, u1, src);
+      xe[a + 16] = __shfl_sync(kFull, u2, src);
+    }
+    mbar_wait(&full[s], phase);
+    const bool active = nid_c >= 0;
+    double r[3] = {0.0, 0.0, 0.0};
+    if (active) {
+      const double2* blk = reinterpret_cast<const double2*>(ring + s * kEaStageBytes + el * kEaElemBytes) + lane;
+#pragma unroll
+      for (int cmp = 0; cmp < 3; ++cmp) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const double2 m = blk[(cmp * 12 + i) * 8];
+          s0 += m.x * xe[2 * i];
+          s1 += m.y * xe[2 * i + 1];
+        }
+        r[cmp] = s0 + s1;
+      }
+    }
+    __syncwarp();
+    {
+      const long tnext = wt + (long)STAGES * stride;
+      if (tnext < nwt) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(tnext, s);
+      }
+    }
+    if (active) {
+      xdoty += u0 * r[0] + u1 * r[1] + u2 * r[2];
+      if (!(msk_c & 1)) red_add_f64(&y[nid_c], r[0]);
+      if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], r[1]);
+      if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], r[2]);
+    }
+    nid_c = nid_n; nid_n = nid_n2;
+    msk_c = msk_n; xc0 = xn0; xc1 = xn1; xc2 = xn2;
+    if (++s == STAGES) { s = 0; phase ^= 1; }
+  }
+  if (dot_accum) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) xdoty += __shfl_xor_sync(kFull, xdoty, m);
+    if (l32 == 0) red_add_f64(dot_accum, xdoty);
+  }
+}
+
 // EA AssembleDiagonal (src/mechanics_operator_ext.cpp:228-265): diag of the element matrices.
-template <int MODE>
+template <int MODE, bool PRIV = false>
 __global__ void __launch_bounds__(256) k_ea_diag(const double* __restrict__ ea, double* __restrict__ diag, ElemIO io,
                                                  long nelems) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -958,7 +1085,8 @@ __global__ void __launch_bounds__(256) k_ea_diag(const double* __restrict__ ea, 
 #pragma unroll
   for (int cmp = 0; cmp < 3; ++cmp) {
     const int j = an + 8 * cmp;
-    const double v = ea[e * 576 + (long)j * 24 + j];
+    const int pv = cmp * 24 + j;  // private layout: entry (row j) of this lane's column j
+    const double v = PRIV ? ea[e * 576 + ((pv >> 1) * 8 + lane) * 2 + (pv & 1)] : ea[e * 576 + (long)j * 24 + j];
     if (MODE == LVEC) red_add_f64(&diag[cmp * io.nnodes + io.e2n[e * 8 + an]], v);
     else diag[e * 24 + j] = v;
   }

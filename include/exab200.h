@@ -155,7 +155,9 @@ long exab200_launch_count(const exab200_ctx* ctx);
  *     whenever the bound J array is the one that call wrote): 20: 4x2, 21: 4x3, 22: 8x2, 23: 4x4, 24: 2x3, 25: 3x3,
  *     26: 2x2 (default, 6 CTAs/SM), 27: 1x2, 28: 1x3, 29: 3x2;  99: disable the rebuilt-J path;  98 / 97: L2
  *     evict_first hint on the operand stream on / off;
- *   compact tangent records (tiled, swizzled TMA): 30: 2x2 (default, 6 CTAs/SM), 31: 2x3, 32: 4x2, 33: 1x2, 34: 2x4, 35: 1x3.
+ *   compact tangent records (tiled, swizzled TMA): 30: 2x2 (default, 6 CTAs/SM), 31: 2x3, 32: 4x2, 33: 1x2, 34: 2x4, 35: 1x3;
+ *   element-matrix apply of the L-vector EA path (bulk TMA pipeline): 40: 2x2 (default, 3 CTAs/SM), 41: 1x2, 42: 1x3,
+ *     43: 2x3;  49: the plain (non-pipelined) kernel.
  *   variant + 100*k additionally sets the material-update occupancy target to k CTAs/SM. */
 int exab200_set_tuning(exab200_ctx* ctx, int ctas_per_sm, int variant);
 

@@ -20,6 +20,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
 
 
+def test_host_library_exports_every_declared_symbol():
+    import ctypes as C
+    import __graft_entry__ as ge
+    ge.build()
+    from exaconstit_b200 import host
+    lib = host.lib()
+    header = open(os.path.join(ROOT, "include", "exahost.h")).read()
+    declared = set(re.findall(r"\b(exahost_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 18
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert os.access(os.path.join(ROOT, "exaconstit_b200", "lib", "mechanics"), os.X_OK)
+
+
 def test_bad_config_is_rejected_before_touching_the_gpu():
     import numpy as np
     from exaconstit_b200 import capi

@@ -115,6 +115,45 @@ def main():
     res["grad_diag"] = dict(ms=t_med, GBps=ne * 3072 / t_med / 1e6)
     t_med, _ = timeit(lambda: ctx.setup_jacobians(xbeg, vel, dt, jac))
     res["jacobians"] = dict(ms=t_med, GBps=ne * 576 / t_med / 1e6)
+    # ---- B-bar residual, element assembly path (config 5) and the HCP material update ----
+    ctx_ea = capi.Context(0, 0, props, 298.0, ne, nn, e2n, 1, 1)
+    ctx_ea.set_essential_mask(mask)
+    t_med, _ = timeit(lambda: ctx_ea.residual(jac, s1, r))
+    res["residual_bbar"] = dict(ms=t_med, GBps=ne * 1152 / t_med / 1e6)
+    t_med, _ = timeit(lambda: ctx_ea.grad_setup(dt, mg, jac), iters=5, warm=1)
+    res["assemble_ea_bbar (incl. memset)"] = dict(ms=t_med, GBps=ne * (4608 + 8 * 45 * 8) / t_med / 1e6)
+    y_ref = None
+    for ctas, var in [(3, 40), (2, 40), (6, 41), (4, 41), (4, 42), (2, 43), (1, 49)]:
+        ctx_ea.set_tuning(ctas, var)
+        t_med, t_min = timeit(lambda: ctx_ea.grad_mult(x, y), iters=20, warm=3)
+        res["ea_mult_v%d_c%d" % (var, ctas)] = dict(ms=t_med, ms_min=t_min, GBps=ne * 4992 / t_med / 1e6, frac=ne * 4992 / t_med / 1e6 / peak)
+        if y_ref is None:
+            y_ref = y.clone()
+        else:
+            assert float((y - y_ref).abs().max() / y_ref.abs().max()) < 1e-13
+    ctx_ea.set_tuning(3, 40)
+    t_med, _ = timeit(lambda: ctx_ea.grad_diag(r))
+    res["ea_diag"] = dict(ms=t_med, GBps=ne * (576 * 8 + 192) / t_med / 1e6)
+    ctx_ea.close()
+    del ctx_ea
+    if N <= 64:
+        hprops = refcases.hcp_props()
+        ctx_h = capi.Context(2, 2, hprops, 298.0, ne, nn, e2n, 1, 1)
+        nsh = ctx_h.nstatev
+        hh0 = torch.zeros(ne * 8, nsh, **f64)
+        hh0[:, 9:13] = q.repeat_interleave(8, dim=0)
+        hh0 = hh0.reshape(-1).contiguous()
+        ctx_h.hist_init(hh0)
+        sh0 = torch.zeros(ne * 48, **f64)
+        sh1, hh1 = torch.empty_like(sh0), torch.empty_like(hh0)
+        for _ in range(3):
+            ctx_h.model_setup(dt * 3, jac, vel, sh0, hh0, sh1, hh1, mg)
+            sh0, sh1 = sh1, sh0
+            hh0, hh1 = hh1, hh0
+        print("HCP failed points:", ctx_h.failed_points())
+        t_med, _ = timeit(lambda: ctx_h.model_setup(dt, jac, vel, sh0, hh0, sh1, hh1, mg), iters=5, warm=1)
+        res["model_setup_hcp_kmbald"] = dict(ms=t_med, qpt_per_s=ne * 8 / t_med * 1e3, GBps=ne * 8 * 1120 / t_med / 1e6)
+        ctx_h.close()
     t_med, _ = timeit(lambda: y.copy_(x))
     res["copy_vec"] = dict(ms=t_med, GBps=2 * 3 * nn * 8 / t_med / 1e6)
     big = torch.empty(ne * 8 * 36, **f64)
