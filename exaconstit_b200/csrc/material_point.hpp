@@ -399,10 +399,11 @@ EXAB_HD bool lu_solve_reg(const double* J, double* b, const double* R, double* g
   }
   return !bad;
 }
-// Same factorisation written back in place: L multipliers below the diagonal, U above, 1/u_ii on it.
+// Same factorisation written back in place (L multipliers below the diagonal, U above, 1/u_ii on it) -- but only
+// after it has succeeded: on a growth failure J is left untouched for the pivoted fallback.
 template <int JS>
 EXAB_HD bool lu_factor_reg_store(double* J) {
-  double U[8][8], inv[8];
+  double U[8][8], L[8][8], inv[8];
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -413,7 +414,7 @@ EXAB_HD bool lu_factor_reg_store(double* J) {
     for (int k = 0; k < i; ++k) {
       const double f = a[k] * inv[k];
       bad |= !(fabs(f) <= kGrowthMax);
-      J[EXAB_JIDX(i, k)] = f;
+      L[i][k] = f;
 #pragma unroll
       for (int j = k + 1; j < 8; ++j) a[j] -= f * U[k][j];
     }
@@ -421,11 +422,17 @@ EXAB_HD bool lu_factor_reg_store(double* J) {
     for (int j = i; j < 8; ++j) U[i][j] = a[j];
     inv[i] = 1.0 / a[i];
     bad |= !(fabs(inv[i]) <= 1.0e300);
+  }
+  if (bad) return false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) J[EXAB_JIDX(i, k)] = L[i][k];
     J[EXAB_JIDX(i, i)] = inv[i];
 #pragma unroll
-    for (int j = i + 1; j < 8; ++j) J[EXAB_JIDX(i, j)] = a[j];
+    for (int j = i + 1; j < 8; ++j) J[EXAB_JIDX(i, j)] = U[i][j];
   }
-  return !bad;
+  return true;
 }
 // NR right-hand sides r[c][0..7] solved at once from the stored factors (each factor entry is read once)
 template <int JS, int NR>
@@ -926,12 +933,29 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
   h1[iH_H] = h_u;
   h1[ind_vols] = vNew;
   // ---- stress out ----
+  // 5x5 rotation of deviatoric 5-vectors for the end-of-step orientation: lattice -> sample is R5 v, sample -> lattice
+  // is R5^T v.  Built once (one copy of the tensor rotation in the code) and reused for the stress and the tangent.
+  double R5[5][5];
+#pragma unroll 1
+  for (int j = 0; j < 5; ++j) {
+    double ej[5] = {0, 0, 0, 0, 0}, colj[5];
+    ej[j] = 1.0;
+    rot_vecd<false>(prob.C, ej, colj);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) R5[i][j] = colj[i];
+  }
   double sig_lat[5], sig_sm[5], s6[6];
 #pragma unroll
   for (int i = 0; i < 5; ++i) sig_lat[i] = prob.detVi * m.Kdiag[i] * prob.e_f[i];
   sig_lat[1] += prob.detVi * prob.T1_shift;
   const double p_tot = pEOS - m.Kvd * prob.e_f[1] * prob.detVi / sqr3;  // hexagonal: c-axis strain carries pressure
-  rot_vecd<false>(prob.C, sig_lat, sig_sm);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) t += R5[i][j] * sig_lat[j];
+    sig_sm[i] = t;
+  }
   vecd_to_svec(sig_sm, s6);
   dEDev += halfVMidDt * (s6[0] * d_svec_p[0] + s6[1] * d_svec_p[1] + s6[2] * d_svec_p[2] +
                          2.0 * (s6[3] * d_svec_p[3] + s6[4] * d_svec_p[4] + s6[5] * d_svec_p[5]));
@@ -940,27 +964,24 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
   s1[3] = s6[3]; s1[4] = s6[4]; s1[5] = s6[5];
   // ---- algorithmic tangent by implicit differentiation through the converged Jacobian ----
   {
-    // right-hand sides: column c = eps_si * (row c of the 5x5 rotation) on the strain rows, 0 on the rotation rows
+    int piv[8];
+    bool ok = !m.force_pivot && lu_factor_reg_store<JS>(J);
+    const bool pivoted = !ok;
+    if (pivoted) {
+      EXAB_STAT(6);
+      ok = lu_factor8<JS>(J, piv);  // J is intact: the register factorisation only writes on success
+    }
+    // right-hand sides: column c = eps_si * (row c of R5) on the strain rows, 0 on the rotation rows
     double r[5][8];
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-      double ec[5] = {0, 0, 0, 0, 0};
-      ec[c] = 1.0;
-      rot_vecd<true>(prob.C, ec, r[c]);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) r[c][i] *= prob.eps_si;
+      for (int i = 0; i < 5; ++i) r[c][i] = prob.eps_si * R5[c][i];
       r[c][5] = r[c][6] = r[c][7] = 0.0;
     }
-    bool ok = !m.force_pivot && lu_factor_reg_store<JS>(J);
-    if (ok) {
+    if (!pivoted) {
       lu_solve_stored<JS, 5>(J, r);
     } else {
-      EXAB_STAT(6);
-      // pivoted fallback; the register factorisation may have overwritten J: rebuild it first
-      double Rd[8];
-      prob.eval(m, x, Rd, J, true, nullptr);
-      int piv[8];
-      ok = lu_factor8<JS>(J, piv);
       for (int c = 0; c < 5; ++c) {
         if (ok) lu_solve8<JS>(J, piv, r[c]);
         else for (int i = 0; i < 8; ++i) r[c][i] = 0.0;
@@ -986,7 +1007,13 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
 #pragma unroll
       for (int j = 0; j < 5; ++j)
         dl[j] = prob.detVi * m.Kdiag[j] * e_scale * r[c][j] - (Msl[j][0] * jr[0] + Msl[j][1] * jr[1] + Msl[j][2] * jr[2]);
-      rot_vecd<false>(prob.C, dl, col);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) t += R5[i][j] * dl[j];
+        col[i] = t;
+      }
 #pragma unroll
       for (int i = 0; i < 5; ++i) dsd[i][c] = col[i] * idt;
     }
@@ -1023,9 +1050,9 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
       hexa[3] = 0.5 * f * sqr2 * s1c[4];
       hexa[4] = 0.5 * f * sqr2 * s1c[3];
       hexa[5] = 0.5 * f * sqr2 * s1c[2];
-      const double e1[5] = {0.0, kc, 0.0, 0.0, 0.0};
       double e1sm[5];
-      rot_vecd<false>(prob.C, e1, e1sm);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) e1sm[i] = kc * R5[i][1];
       vecd_to_svec(e1sm, hexb);
     }
 #pragma unroll
