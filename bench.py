@@ -187,11 +187,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "qpt_updates_per_sec": (ne_local * 8 * nranks) / (k1_ms * 1e-3) if ms_cnt else None,
             "pa_mult_GBps_per_gpu": achieved,
-            "roofline": {"kernel": "k_grad_mult_pa_w<2,2,LVEC,ESS,JX> (PA gradient apply, Jacobians rebuilt from coordinates; timed with its output memset)", "bound": "hbm",
+            "roofline": {"kernel": "k_grad_mult_pa_c<2,2,ESS> (PA gradient apply: compact tangent records via tiled TMA, Jacobians rebuilt from coordinates)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": TRAFFIC_NCU.get(n) if nranks == 1 else None,
                          "algorithmic_bytes_per_launch": ne_local * ALG_BYTES_PA_APPLY,
+                         # the same launch time against the bytes the kernel really moves (ncu): the algorithmic figure
+                         # counts the 36-entry tangent and the Jacobians, which the default kernel no longer reads
+                         "dram_frac": (TRAFFIC_NCU[n] / (apply_ms * 1e-3) / 1e9 / peak) if (nranks == 1 and n in TRAFFIC_NCU and gm_cnt) else None,
                          "launches_timed": int(gm_cnt), "avg_launch_ms": apply_ms,
                          "share_of_step": gm_ms / dev_ms},
             "model_setup": {"avg_ms": k1_ms, "calls": int(ms_cnt), "share_of_step": ms_ms / dev_ms,

@@ -326,7 +326,7 @@ struct KernelTimer {
 // Mailbox layout (doubles): [0,64) flags as u64: 0 halo-from-lo, 1 halo-from-hi, 8+r scalar-from-rank-r,
 // 16 block counter, 17 error;  [64,192) scalar slots [par][rank][8];  [192, 192+12*plane) halo slots
 // [from-lo | from-hi][par][3*plane].
-constexpr int kMbFlags = 0, kMbScal = 64, kMbHalo = 192;
+constexpr int kMbScal = 64, kMbHalo = 192;
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s: turn a lost peer into an error instead of a hang
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
