@@ -86,3 +86,29 @@ def test_slab_partition_covers_mesh():
         lays = [parallel.SlabLayout(3, 2, nz, r, nr) for r in range(nr)]
         assert sum(l.nelems for l in lays) == 3 * 2 * nz
         assert sum(l.n_owned for l in lays) == 4 * 3 * (nz + 1)
+
+
+def test_slab_bc_masks_tile_the_global_masks():
+    """Essential / velocity-gradient masks and prescribed values built per z-slab (what each rank hands to
+    exahost_set_bcs / exahost_set_vgrad) agree with the global ones on every node, duplicated interface planes
+    included."""
+    from exaconstit_b200 import voxel
+    nx, ny, nz, nranks = 4, 3, 7, 3
+    ids, comps = [1, 2, 3, 4, 6], [3, -1, -2, -3, 7]
+    vals = np.arange(15, dtype=float).reshape(5, 3)
+    gm, gv = voxel.essential_bcs(nx, ny, nz, ids, comps, vals)
+    gg = voxel.vgrad_mask(nx, ny, nz, ids, comps)
+    plane = (nx + 1) * (ny + 1)
+    z0 = voxel.slab_partition(nz, nranks)
+    assert z0[0] == 0 and z0[-1] == nz and np.all(np.diff(z0) >= 2)
+    nn_g = plane * (nz + 1)
+    for r in range(nranks):
+        nzl = int(z0[r + 1] - z0[r])
+        m, v = voxel.essential_bcs(nx, ny, nzl, ids, comps, vals, int(z0[r]), nz)
+        g = voxel.vgrad_mask(nx, ny, nzl, ids, comps, int(z0[r]), nz)
+        lo, hi = int(z0[r]) * plane, (int(z0[r]) + nzl + 1) * plane
+        assert np.array_equal(m, gm[lo:hi]) and np.array_equal(g, gg[lo:hi])
+        nn_l = plane * (nzl + 1)
+        for d in range(3):
+            assert np.array_equal(v[d * nn_l:(d + 1) * nn_l], gv[d * nn_g + lo:d * nn_g + hi])
+    assert np.all((gg & ~gm) == 0)      # velocity-gradient dofs are a subset of the essential ones
