@@ -64,3 +64,30 @@ def test_missing_input_file_aborts(tmp_path):
     r = subprocess.run([app_inputs.mechanics_binary(), "-opt", "options.toml", "--check"], cwd=str(tmp_path),
                        capture_output=True, text=True)
     assert r.returncode != 0 and "Cannot open grain map file" in r.stderr
+
+
+def test_option_reader_toml_subset_edge_cases(tmp_path):
+    """constructs the reference's files use that are easy to get wrong: '#' inside strings, comments inside multi-line
+    arrays, trailing commas, integers where floats are expected, underscores in numbers, exponents without a dot"""
+    import __graft_entry__ as ge
+    ge.build()
+    opt = app_inputs.write_case(str(tmp_path))
+    txt = open(opt).read()
+    txt = txt.replace('avg_stress_fname = "test_stress.txt"', 'avg_stress_fname = "stress#1.txt"   # a comment')
+    txt = txt.replace("iter = 25", "iter = 2_5")
+    txt = txt.replace("rel_tol = 5e-05", "rel_tol = 5E-5")
+    txt = txt.replace("length = [1.0, 1.0, 1.0]", "length = [1, 1,   # integers, and a comment inside the array\n   1,]")
+    txt = txt.replace("temperature = 298", "temperature = 3.0e2")
+    open(opt, "w").write(txt)
+    r = subprocess.run([app_inputs.mechanics_binary(), "-opt", opt, "--check"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "files stress#1.txt" in r.stdout
+    assert "nr 5e-05 5e-10 25" in r.stdout and "temp 300" in r.stdout
+    # unsupported TOML constructs are rejected loudly, not mis-parsed
+    bad = txt.replace('[Mesh.Auto]', '[Mesh.Auto]\n        point = { x = 1, y = 2 }')
+    open(opt, "w").write(bad)
+    r = subprocess.run([app_inputs.mechanics_binary(), "-opt", opt, "--check"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode != 0 and "inline tables are not supported" in r.stderr
+    open(opt, "w").write(txt.replace("[Solvers]", "[[Solvers]]"))
+    r = subprocess.run([app_inputs.mechanics_binary(), "-opt", opt, "--check"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode != 0 and "bad table header" in r.stderr
