@@ -150,13 +150,6 @@ inline std::string build_material(MatDev& m, int xtal, int kin, const double* p,
     const double n = m.xmi - 1.0;
     m.pl_n = (n >= 1.0 && n <= 512.0 && n == std::floor(n)) ? (int)n : 0;
   }
-  // products used by the Jacobian accumulation: d D^p = sum dg P(x)P, d W^p = sum dg Q(x)P
-  for (int a = 0; a < m.nslip; ++a) {
-    for (int i = 0; i < 5; ++i)
-      for (int j = i; j < 5; ++j) m.PP[a][mat::sidx(i, j)] = m.P[a][i] * m.P[a][j];
-    for (int k = 0; k < 3; ++k)
-      for (int j = 0; j < 5; ++j) m.QP[a][k * 5 + j] = m.Q[a][k] * m.P[a][j];
-  }
   m.ln_ovf = std::log(1.0e45);
   m.gruneisen = p[i++];
   const double ec0 = p[i++];

@@ -17,8 +17,8 @@
 // Design for the SM (one thread = one point):
 //   * the material description is a kernel parameter (constant bank): with the 12-system loops fully
 //     unrolled every Schmid-tensor entry is an immediate constant operand of a DFMA -- no loads;
-//   * d D^p / d tau and d W^p / d tau are accumulated through the precomputed products P(x)P (15 unique
-//     entries) and Q(x)P (15) instead of 40 products per system;
+//   * d D^p / d tau and d W^p / d tau are accumulated as (dg P)(x)P (15 unique entries) and Q(x)(dg P) (15)
+//     instead of 40 products per system, from the same 8 table entries the D^p / W^p sums use;
 //   * integer power-law exponents (1/m - 1 = 49 for the reference's Voce parameters) are evaluated by
 //     repeated squaring for all systems at once instead of exp(n log x) per system;
 //   * the 8x8 Newton system is factored in registers (row-wise Doolittle, 36 doubles of U live) straight
@@ -72,8 +72,6 @@ struct MatDev {
   int pad_;
   double P[kMaxSlip][5];
   double Q[kMaxSlip][3];
-  double PP[kMaxSlip][15];  // P_i P_j, i <= j, packed by sidx()
-  double QP[kMaxSlip][15];  // Q_k P_j at [k*5 + j]
   double Kdiag[5], bulk, gmod, Kvd;  // Kvd: hexagonal volumetric <-> c-axis deviator coupling (0 for cubic)
   double tol, gruneisen, dtde, tK0;
   // Voce power law
@@ -494,6 +492,26 @@ struct Point {
     }
   }
 
+  // One slip system's contribution: D^p += gd P, W^p += gd Q and the tangent sums S += dg P (x) P (15 unique entries),
+  // Wq += dg Q (x) P, all from the same 8 table entries (on sm_100a every constant operand of a DFMA costs an LDCU
+  // into a uniform register first, so the entries are loaded once and v = dg P is formed explicitly)
+  EXAB_HD static void accumulate_slip(const MatDev& m, int a, double gd, double dg, double* dp, double* wp, double* S,
+                                      double* Wq) {
+    double Pa[5], Qa[3], v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { Pa[i] = m.P[a][i]; v[i] = dg * Pa[i]; dp[i] += gd * Pa[i]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Qa[k] = m.Q[a][k]; wp[k] += gd * Qa[k]; }
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = i; j < 5; ++j) S[sidx(i, j)] += v[i] * Pa[j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) Wq[k * 5 + j] += Qa[k] * v[j];
+  }
+
   // Residual R[8] at the scaled unknowns x; with want_jac also the 8x8 Jacobian into J; with gout != nullptr
   // the slip rates are written there.  e_f, q_f, C, shrate, disRate describe the evaluated state.
   EXAB_HD void eval(const MatDev& m, const double* x, double* R, double* J, bool want_jac, double* gout) {
@@ -584,19 +602,7 @@ EXAB_UNROLL_SLIP
         }
         if (gout) gout[a] = gd;
         shrate += fabs(gd);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) dp[i] += gd * m.P[a][i];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) wp[k] += gd * m.Q[a][k];
-        tt[a] = dg;
-      }
-      if (want_jac) {
-EXAB_UNROLL_SLIP
-        for (int a = 0; a < NSLIP; ++a) {
-          const double dg = tt[a];
-#pragma unroll
-          for (int n = 0; n < 15; ++n) { S[n] += dg * m.PP[a][n]; Wq[n] += dg * m.QP[a][n]; }
-        }
+        accumulate_slip(m, a, gd, dg, dp, wp, S, Wq);
       }
     } else {
 #pragma unroll 1
@@ -608,14 +614,7 @@ EXAB_UNROLL_SLIP
         kin_kmbald(m, gv(a), gam_w, gam_r, cev(a), tau, gd, dg);
         if (gout) gout[a] = gd;
         shrate += fabs(gd);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) dp[i] += gd * m.P[a][i];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) wp[k] += gd * m.Q[a][k];
-        if (want_jac) {
-#pragma unroll
-          for (int n = 0; n < 15; ++n) { S[n] += dg * m.PP[a][n]; Wq[n] += dg * m.QP[a][n]; }
-        }
+        accumulate_slip(m, a, gd, dg, dp, wp, S, Wq);
       }
     }
     // plastic dissipation rate sum_a tau_a gdot_a = T . D^p
