@@ -154,7 +154,7 @@ class VoxelSim {
   ecm::Material mat;
   long ne, nn, ndof;
   std::vector<int> e2n;
-  dvec x_beg, x_end, G, W;
+  dvec x_beg, x_end, x_ref, G, W;
   dvec stress0, stress1, hist0, hist1, matgrad;
   dvec jac, velE, c81, D81, ea, eds, dres;
   std::vector<char> ess;    // per true dof
@@ -175,6 +175,7 @@ class VoxelSim {
     x_beg.resize(ndof);
     voxel_mesh(c.nx, c.ny, c.nz, c.len[0], c.len[1], c.len[2], e2n.data(), x_beg.data());
     x_end = x_beg;
+    x_ref = x_beg;
     G.resize(192);
     W.resize(8);
     hex8_dshape(G.data(), W.data());
@@ -548,6 +549,17 @@ class VoxelSim {
           for (int i = 0; i < 6; ++i) dp[p * 6 + i] = s6[i];
         }
         vol_avg(dp, 6, &ex[1], true);
+        // <F>: CalculateDeformationGradient (src/mechanics_operator.cpp:393-427): gradient of the current coordinates
+        // with respect to the REFERENCE mesh at its quadrature points, F(i,t) at [t*3+i]; averaged over the
+        // current mesh like the other quantities (src/system_driver.cpp:496-517) -> ex[7..15]
+        {
+          dvec xrE(ne * 24), xcE(ne * 24), jref(npts * 9), F(npts * 9, 0.0);
+          gather(ne, nn, e2n.data(), x_ref.data(), xrE.data());
+          jacobians(ne, G.data(), xrE.data(), jref.data());
+          gather(ne, nn, e2n.data(), x_beg.data(), xcE.data());
+          grad_calc(ne, jref.data(), G.data(), xcE.data(), F.data());
+          vol_avg(F, 9, &ex[7], true);
+        }
       }
       if (iters) { iters[(ti - 1) * 2] = nit; iters[(ti - 1) * 2 + 1] = (int)(stats.pcg_iters - pcg0); }
       if (last_step) break;

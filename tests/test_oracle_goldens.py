@@ -51,6 +51,18 @@ def test_plastic_work_and_dp_goldens(orc):
     dp = r["extra"][:8, 1:7]
     gd = g["voce_ea_dp_tensor"][:8]
     assert np.abs(dp - gd).max() / np.abs(gd).max() < 2e-4
+    # volume-averaged deformation gradient (voce_ea_def_grad.txt, values ~1 printed with 6 digits)
+    assert np.abs(r["extra"][:8, 7:16] - g["voce_ea_def_grad"][:8]).max() < 6e-6
+
+
+def test_additional_averages_constant_strain_rate(orc):
+    """voce_ea_cs_{pl_work,dp_tensor,def_grad}.txt: the additional averages under velocity-gradient BCs"""
+    g = refcases.goldens()
+    r, gold = _run(orc, "voce_ea_cs", 10)
+    gp, gd, gF = g["voce_ea_cs_pl_work"][:10], g["voce_ea_cs_dp_tensor"][:10], g["voce_ea_cs_def_grad"][:10]
+    assert np.abs(r["extra"][:10, 0] - gp).max() / np.abs(gp).max() < 2e-4
+    assert np.abs(r["extra"][:10, 1:7] - gd).max() / np.abs(gd).max() < 2e-4
+    assert np.abs(r["extra"][:10, 7:16] - gF).max() < 6e-6
 
 
 def test_cyclic_reversal(orc):
