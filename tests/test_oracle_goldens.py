@@ -33,7 +33,7 @@ def test_voce_pa_full_history(orc):
     assert r["stats"]["newton_iters"] < 120
 
 
-@pytest.mark.parametrize("name,nsteps", [("voce_ea", 8), ("voce_bcc", 8), ("voce_nl_full", 6), ("mtsdd_bcc", 10),
+@pytest.mark.parametrize("name,nsteps", [("voce_ea", 8), ("voce_full", 8), ("voce_bcc", 8), ("voce_nl_full", 6), ("mtsdd_bcc", 10),
                                          ("mtsdd_full", 10)])
 def test_other_cases_prefix(orc, name, nsteps):
     r, gold = _run(orc, name, nsteps)
