@@ -16,7 +16,8 @@
 //
 // Design for the SM (one thread = one point):
 //   * the material description is a kernel parameter (constant bank): with the 12-system loops fully
-//     unrolled every Schmid-tensor entry is an immediate constant operand of a DFMA -- no loads;
+//     unrolled every Schmid-tensor entry has a compile-time address and reaches the DFMAs through one uniform
+//     load (LDCU into a uniform register; sm_100a DFMAs take no constant-bank operand) -- no per-thread loads;
 //   * d D^p / d tau and d W^p / d tau are accumulated as (dg P)(x)P (15 unique entries) and Q(x)(dg P) (15)
 //     instead of 40 products per system, from the same 8 table entries the D^p / W^p sums use;
 //   * integer power-law exponents (1/m - 1 = 49 for the reference's Voce parameters) are evaluated by
