@@ -24,7 +24,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DT_SCHEDULE = [0.005, 0.195, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1]
+# the 40-step schedule of the reference's regression suite (test/data/custom_dt.txt, used by test/data/voce_pa.toml)
+DT_SCHEDULE = [0.005, 0.195] + [0.1] * 19 + [0.2] * 6 + [0.4] * 4 + [0.2, 0.6, 0.5, 0.5, 0.75, 0.75, 0.75, 0.75, 1.0]
+assert len(DT_SCHEDULE) == 40
+
+
+def dt_schedule(nsteps):
+    """Step sizes of a run of `nsteps` steps: the reference schedule, its last entry repeated if the run outlasts it."""
+    return [DT_SCHEDULE[min(i, len(DT_SCHEDULE) - 1)] for i in range(nsteps)]
+
+
+# BASELINE.json configs 2-4 (SURVEY.md 8d): grain count and Voronoi seed by mesh size; other sizes keep the grain
+# density of the 128^3 workload
+def grains_for(n, grains=None):
+    known = {32: (100, 32100), 64: (500, 64500), 128: (2000, 1282000)}
+    g, seed = known.get(n, (max(4, (2000 * n ** 3) // 128 ** 3), 1000 * n + 7))
+    return (grains if grains else g), seed
+
 # FCC Voce property vector of the reference's regression suite (test/data/props_cp_voce.txt)
 PROPS_VOCE = [8.920e-6, 0.003435984, 1.0e-10, 168.4, 121.4, 75.2, 44.0, 0.02, 1.0, 400.0e-3, 17.0e-3, 122.4e-3, 0.0,
               5.0e9, 17.0e-3, 0.0, -1.0307952]
@@ -115,7 +131,8 @@ def run_ours(args):
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().tolist())
     n = args.n
-    grains, quats = workload(n, args.grains, 1282000)
+    ngrains, seed = grains_for(n, args.grains)
+    grains, quats = workload(n, ngrains, seed)
     sim = host.VoxelSim((n, n, n), (1.0, 1.0, 1.0), 0, 0, PROPS_VOCE, 298.0, grains, quats, assembly=0,
                         nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, args.krylov_iter), true_jacobi=args.true_jacobi,
                         rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
@@ -135,10 +152,11 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     steps = []
-    dts = DT_SCHEDULE
-    assert args.warmup + args.steps <= len(dts), "dt schedule has %d steps" % len(dts)
+    dts = dt_schedule(args.warmup + args.steps)
     for i in range(args.warmup):
         steps.append(sim.step(dts[i], bc_changed=(i == 0), ess_val_host=ess_pinned, vel_out_host=vel_out))
+        if not steps[-1]["converged"]:
+            raise SystemExit("bench.py: Newton did not converge in warm-up step %d" % (i + 1))
     sim.kernel_timing(True)
     sim.kernel_time("grad_mult", reset=True)
     sim.kernel_time("model_setup", reset=True)
@@ -177,8 +195,7 @@ def run_ours(args):
             "metric": "newton_steps_per_sec", "value": newton / (dev_ms * 1e-3), "unit": "Newton-steps/s",
             "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%d^3 voxel, %d Voronoi grains, FCC Voce, PA + PCG (identity smoother, %d-iter cap), "
-                                   "uniaxial velocity BC" % (n, args.grains, args.krylov_iter),
+            "config": {"workload": WORKLOAD_FMT % (n, ngrains, args.krylov_iter),
                        "mesh": [n, n, n], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi),
                        "cache": "inputs >> L2 (%.1f GB of quadrature data per rank)" % (ne_local * 8 * (36 + 9 + 2 * 28 + 12) * 8 / 1e9),
                        "newton_iters": newton, "pcg_iters": pcg, "model_setups": setups, "grad_mults": gmults},
@@ -201,15 +218,63 @@ def run_ours(args):
                             "GBps_algorithmic": ne_local * 8 * ALG_BYTES_QPT_UPDATE / (k1_ms * 1e-3) / 1e9 if ms_cnt else None},
             "clocks": clocks,
             "avg_stress_zz_last": float(timed[-1]["avg_stress"][2]),
+            "all_steps_converged": bool(all(s["converged"] for s in timed)),
             "wall_ms": wall_ms,
         }
         if nranks == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(n, pcg / max(newton, 1), setups / max(newton, 1), budget_s=args.cpu_budget)
+            out["cpu_baseline"] = cpu_baseline(n, args.krylov_iter, args.warmup, budget_s=args.cpu_budget)
+        out["parity_fingerprint"] = check_fingerprint(n, ngrains, args, steps + timed)
+        sim.close()
+        sim = None
+        if nranks == 1 and not args.no_same_config:
+            # the same time steps on the sample meshes the CPU arm may pick: an un-extrapolated GPU/CPU pair
+            # (compare with the reference arm's config.newton_steps_per_sec_on_sample at its config.sample_mesh)
+            out["config"]["newton_steps_per_sec_on_sample_meshes"] = {
+                str(m): gpu_sample_run(host, m, args, local) for m in CPU_SAMPLE_MESHES}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
-    sim.close()
+    if sim is not None:
+        sim.close()
     if nranks > 1:
         dist.destroy_process_group()
+
+
+def gpu_sample_run(host, m, args, device):
+    """e2e Newton-steps/s of the GPU path on an m^3 sample mesh over the timed steps of the schedule (host buffers in and
+    out every step, like the main run)."""
+    g, seed = grains_for(m)
+    grains, quats = workload(m, g, seed)
+    sim = host.VoxelSim((m, m, m), (1.0, 1.0, 1.0), 0, 0, PROPS_VOCE, 298.0, grains, quats, assembly=0,
+                        nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, args.krylov_iter), true_jacobi=args.true_jacobi, device=device)
+    _, ess_val = sim.set_bcs(*BC)
+    vel_out = np.zeros(3 * sim.nnodes)
+    dts = dt_schedule(args.warmup + args.steps)
+    rs = [sim.step(dts[i], bc_changed=(i == 0), ess_val_host=ess_val, vel_out_host=vel_out) for i in range(len(dts))]
+    sim.close()
+    timed = rs[args.warmup:]
+    return sum(r["newton_iters"] for r in timed) / (sum(r["e2e_ms"] for r in timed) * 1e-3)
+
+
+FINGERPRINT = os.path.join(ROOT, "tests", "golden", "bench_fingerprint.json")
+
+
+def check_fingerprint(n, ngrains, args, steps):
+    """Parity evidence inside the bench: the volume-averaged stress history of this run (any number of ranks) against
+    the stored 1-GPU history of the same workload (tools/make_bench_fingerprint.py), relative to the step's largest
+    component.  The 1-GPU history itself is tied to the oracle by tests/test_gpu_system.py at 8^3 and 32^3."""
+    if not os.path.exists(FINGERPRINT):
+        return {"checked": False, "why": "no fingerprint file"}
+    fp = json.load(open(FINGERPRINT))
+    key = "%d:%d:%d:%d" % (n, ngrains, args.krylov_iter, int(args.true_jacobi))
+    if key not in fp:
+        return {"checked": False, "why": "no stored history for " + key}
+    ref = np.array(fp[key]["avg_stress"])
+    got = np.array([s["avg_stress"] for s in steps])
+    m = min(len(ref), len(got))
+    err = float(np.max(np.abs(got[:m] - ref[:m]).max(axis=1) / np.abs(ref[:m]).max(axis=1)))
+    newton_same = [int(s["newton_iters"]) for s in steps[:m]] == [int(x) for x in fp[key]["newton_iters"][:m]]
+    return {"checked": True, "steps_compared": m, "max_rel_err": err, "tol": 1e-8, "ok": bool(err <= 1e-8),
+            "newton_iters_identical": bool(newton_same), "stored_run": fp[key].get("run", "1 GPU")}
 
 
 # ncu --set full dram bytes (read+write) per K2 launch, filled in from profiles/ (see profiles/README.md)
@@ -219,121 +284,161 @@ if os.path.exists(_tp):
     TRAFFIC_NCU = {int(k): v for k, v in json.load(open(_tp)).items()}
 
 
-def cpu_sample(n_sample, pcg_iters=8, threads=None):
-    """Times the CPU oracle (restatement of the reference algorithm) on an n_sample^3 sub-mesh of the same
-    workload: one ModelSetup, one gradient assembly, `pcg_iters` PA applies + CG vector work."""
-    from oracle import orc
-    from exaconstit_b200 import voxel
-    n = n_sample
-    ne, nn = n ** 3, (n + 1) ** 3
-    e2n, coords = voxel.voxel_mesh(n, n, n)
-    G, W = orc.hex8_dshape()
-    grains = voxel.voronoi_grains(n, n, n, max(2, 2000 * ne // 128 ** 3), 7)
-    quats = voxel.random_quats(int(grains.max()), 8)
-    props = np.array(PROPS_VOCE)
-    nsv = orc.nhist(0, 0)
-    hist0 = np.tile(orc.hist_init(0, 0, props), ne * 8).reshape(ne * 8, nsv)
-    hist0[:, 9:13] = np.repeat(quats[grains - 1], 8, axis=0)
-    hist0 = hist0.ravel().copy()
-    s0 = np.zeros(ne * 48)
-    vel = voxel.uniaxial_velocity(coords, nn, 2e-3)
-    dt = 0.2
-    x = coords.copy()
-    velE = orc.gather(e2n, vel)
-    # two preparatory updates so the timed one is in the plastic regime
-    for _ in range(2):
-        x = x + dt * vel
-        jac = orc.jacobians(G, orc.gather(e2n, x))
-        s0, hist0, _, _ = orc.model_setup(0, 0, props, dt, 298.0, jac, G, velE, s0, hist0)
-    x = x + dt * vel
-    jac = orc.jacobians(G, orc.gather(e2n, x))
-    t = time.perf_counter()
-    s1, h1, mg, nfail = orc.model_setup(0, 0, props, dt, 298.0, jac, G, velE, s0, hist0)
-    t_ms = time.perf_counter() - t
-    t = time.perf_counter()
-    c81 = orc.transform_matgrad_4d(mg)
-    D = np.zeros(ne * 8 * 81)
-    import ctypes as C
-    orc.lib().orc_assemble_grad_pa(C.c_long(ne), C.c_double(dt), orc._p(jac), orc._p(W), orc._p(c81), orc._p(D))
-    t_ga = time.perf_counter() - t
-    xv = np.random.default_rng(0).normal(size=3 * nn)
-    t = time.perf_counter()
-    for _ in range(pcg_iters):
-        xE = orc.gather(e2n, xv)
-        yE = np.zeros(ne * 24)
-        orc.lib().orc_addmult_grad_pa(C.c_long(ne), orc._p(G), orc._p(D), orc._p(xE), orc._p(yE))
-        y = orc.scatter_add(e2n, yE, nn)
-        xv = xv + 1e-9 * y  # CG-like vector traffic
-        _ = float(xv @ y)
-    t_it = (time.perf_counter() - t) / pcg_iters
-    return dict(n=n, ne=ne, t_model_setup=t_ms, t_grad_assembly=t_ga, t_pcg_iter=t_it, threads=orc.num_threads())
+WORKLOAD_FMT = ("%d^3 voxel, %d Voronoi grains, FCC Voce, PA + PCG (identity smoother, %d-iter cap), "
+                "uniaxial velocity BC")
+CPU_SAMPLE_MESHES = (12, 16, 20, 24, 28, 32)
 
 
-def cpu_baseline(n_full, pcg_per_newton, setups_per_newton, budget_s=25.0):
-    n_s = 32
-    s = cpu_sample(n_s)
-    scale = (n_full / n_s) ** 3
-    t_newton = scale * (s["t_model_setup"] * setups_per_newton + s["t_grad_assembly"] + s["t_pcg_iter"] * pcg_per_newton)
-    return {"value": 1.0 / t_newton, "unit": "Newton-steps/s", "cores": s["threads"], "kind": "port",
-            "sample": "CPU restatement of the reference algorithm (oracle/, OpenMP) timed on a %d^3 sub-mesh: 1 ModelSetup "
-                      "%.2fs, 1 AssembleGradPA %.2fs, PA apply+CG vector work %.3fs/iter; scaled x%.0f elements to %d^3 with "
-                      "the GPU run's %.0f PCG iters and %.2f ModelSetups per Newton step"
-                      % (n_s, s["t_model_setup"], s["t_grad_assembly"], s["t_pcg_iter"], scale, n_full, pcg_per_newton,
-                         setups_per_newton),
-            "qpt_updates_per_sec": s["ne"] * 8 / s["t_model_setup"],
-            "pa_mult_GBps_reference_layout": s["ne"] * 5760 / s["t_pcg_iter"] / 1e9}
+class CpuArm:
+    """The CPU restatement of the reference algorithm (oracle/, OpenMP on every host thread this process may use)
+    advancing a REAL simulation of the bench workload on an n_s^3 sample mesh: same material, BCs, dt schedule,
+    solver settings and grain statistics, one SystemDriver::Solve per step (src/mechanics_driver.cpp:982-998 times the
+    same thing).  Nothing here is hand-assembled: iteration counts and times are whatever the solve takes."""
+
+    def __init__(self, n_s, krylov_iter, true_jacobi=False):
+        from oracle import orc
+        from exaconstit_b200 import voxel
+        self.orc = orc
+        self.threads = orc.use_all_host_threads()
+        self.n = n_s
+        g, seed = grains_for(n_s)
+        grains = voxel.voronoi_grains(n_s, n_s, n_s, g, seed)
+        quats = voxel.random_quats(g, seed + 1)
+        self.ngrains = g
+        self.sim = orc.SimStepper((n_s,) * 3, (1.0, 1.0, 1.0), 0, 0, PROPS_VOCE, 298.0, grains, quats, [(1,) + BC], assembly=0,
+                                  nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, krylov_iter), true_jacobi=true_jacobi)
+        self.krylov_iter = krylov_iter
+
+    def run(self, dts):
+        out = []
+        for dt in dts:
+            r = self.sim.step(dt)
+            if r["rc"]:
+                raise RuntimeError("CPU arm: Newton failed on the %d^3 sample" % self.n)
+            out.append(r)
+        return out
+
+    def close(self):
+        self.sim.close()
+
+
+def pick_sample_mesh(nsteps, budget_s, krylov_iter):
+    """Largest sample mesh whose `nsteps` steps fit `budget_s` of CPU time on this host, from a 4-step calibration run
+    on the smallest mesh: a step costs ~ n^3 elements x n CG iterations per solve."""
+    n0 = CPU_SAMPLE_MESHES[0]
+    arm = CpuArm(n0, krylov_iter)
+    t_step = max(r["seconds"] for r in arm.run(dt_schedule(4)))
+    arm.close()
+    best = n0
+    for n in CPU_SAMPLE_MESHES:
+        if nsteps * t_step * (n / n0) ** 4 <= budget_s:
+            best = n
+    return best, t_step
+
+
+def scale_to_full(timed, n_s, n_full, krylov_iter):
+    """Newton-steps/s of the full mesh from the timed steps of the sample: per-element costs scale with the element
+    count; the CG iteration count of the un-preconditioned solve grows like the mesh edge until the iteration cap."""
+    newton = sum(r["newton_iters"] for r in timed)
+    pcg = sum(r["pcg_iters"] for r in timed)
+    t_all = sum(r["seconds"] for r in timed)
+    t_pcg = sum(r["pcg_seconds"] for r in timed)
+    ratio = (n_full / n_s) ** 3
+    pcg_per_newton_s = pcg / max(newton, 1)
+    pcg_per_newton_full = min(float(krylov_iter), pcg_per_newton_s * n_full / n_s)
+    t_newton_full = ratio * ((t_all - t_pcg) / max(newton, 1) + (t_pcg / max(pcg, 1)) * pcg_per_newton_full)
+    return {"value": 1.0 / t_newton_full, "newton_iters": newton, "pcg_iters": pcg, "seconds": t_all, "pcg_seconds": t_pcg,
+            "element_ratio": ratio, "pcg_per_newton_sample": pcg_per_newton_s, "pcg_per_newton_full": pcg_per_newton_full,
+            "newton_steps_per_sec_on_sample": newton / t_all,
+            "model_setups": sum(r["model_setups"] for r in timed)}
+
+
+def sample_text(n_s, n_full, nsteps, first, sc, threads):
+    return ("CPU restatement of the reference algorithm (oracle/, OpenMP, %d threads): %d real time steps (steps %d-%d of the "
+            "schedule) of the same workload on a %d^3 sample mesh: %d Newton iterations, %d CG iterations, %.1f s (%.1f s in CG); "
+            "scaled to %d^3 by x%.0f elements and %.0f CG iterations per Newton iteration (sample: %.0f, grows with the mesh "
+            "edge, capped by the solver's iteration limit)"
+            % (threads, nsteps, first + 1, first + nsteps, n_s, sc["newton_iters"], sc["pcg_iters"], sc["seconds"],
+               sc["pcg_seconds"], n_full, sc["element_ratio"], sc["pcg_per_newton_full"], sc["pcg_per_newton_sample"]))
+
+
+def cpu_baseline(n_full, krylov_iter, warmup, budget_s=25.0):
+    """cpu_baseline leg of our arm (rank 0, N=1): a bounded run of the CPU arm, reported next to the GPU number."""
+    nsteps = 3
+    n_s, _ = pick_sample_mesh(warmup + nsteps, budget_s, krylov_iter)
+    arm = CpuArm(n_s, krylov_iter)
+    dts = dt_schedule(warmup + nsteps)
+    arm.run(dts[:warmup])
+    timed = arm.run(dts[warmup:])
+    arm.close()
+    sc = scale_to_full(timed, n_s, n_full, krylov_iter)
+    return {"value": sc["value"], "unit": "Newton-steps/s", "cores": arm.threads, "kind": "port",
+            "sample": sample_text(n_s, n_full, nsteps, warmup, sc, arm.threads),
+            "sample_mesh": [n_s] * 3, "newton_steps_per_sec_on_sample": sc["newton_steps_per_sec_on_sample"],
+            "qpt_updates_per_sec": None}
 
 
 def run_reference(args):
     """Reference arm: the reference's algorithm on the host CPU cores.  The reference itself cannot be built
-    here (MFEM/ExaCMech/RAJA/MPI absent), so this is the oracle port with all host threads."""
+    here (MFEM/ExaCMech/RAJA/MPI absent), so this is the oracle port with all host threads.  Each step is one real time
+    step of the workload on a sample mesh sized to the time budget; `value` is computed from exactly the timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    counts = {"pcg_per_newton": 1000.0, "setups_per_newton": 1.5}
-    p = os.path.join(ROOT, "profiles", "bench_counts.json")
-    if os.path.exists(p):
-        counts.update(json.load(open(p)))
-    n_s = 32
-    samples = []
-    for _ in range(args.warmup):
-        cpu_sample(16, pcg_iters=2)
+    ngrains, _ = grains_for(args.n, args.grains)
+    nsteps = args.warmup + args.steps
+    n_s = args.ref_n or pick_sample_mesh(nsteps, args.ref_budget, args.krylov_iter)[0]
+    arm = CpuArm(n_s, args.krylov_iter, args.true_jacobi)
+    dts = dt_schedule(nsteps)
+    arm.run(dts[:args.warmup])
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        samples.append(cpu_sample(n_s, pcg_iters=6))
+    timed = arm.run(dts[args.warmup:])
     wall = time.perf_counter() - t0
-    scale = (args.n / n_s) ** 3
-    t_newton = np.mean([scale * (s["t_model_setup"] * counts["setups_per_newton"] + s["t_grad_assembly"]
-                                 + s["t_pcg_iter"] * counts["pcg_per_newton"]) for s in samples])
-    v = 1.0 / t_newton
+    arm.close()
+    sc = scale_to_full(timed, n_s, args.n, args.krylov_iter)
+    v = sc["value"]
     out = {"impl": "reference", "metric": "newton_steps_per_sec", "value": v, "unit": "Newton-steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%d^3 voxel, %d Voronoi grains, FCC Voce, PA + PCG (identity smoother, %d-iter cap), "
-                                  "uniaxial velocity BC" % (args.n, args.grains, args.krylov_iter), "mesh": [args.n] * 3},
-           "cpu_baseline": {"value": v, "unit": "Newton-steps/s", "cores": samples[0]["threads"], "kind": "port",
-                            "sample": "each step = oracle on a %d^3 sub-mesh (1 ModelSetup + 1 AssembleGradPA + 6 PCG iterations), "
-                                      "scaled x%.0f elements with %.0f PCG iters and %.2f ModelSetups per Newton step"
-                                      % (n_s, scale, counts["pcg_per_newton"], counts["setups_per_newton"])},
+           "config": {"workload": WORKLOAD_FMT % (args.n, ngrains, args.krylov_iter), "mesh": [args.n] * 3,
+                      "sample_mesh": [n_s] * 3, "sample_grains": arm.ngrains,
+                      # value = (Newton iterations timed / seconds timed) / slowdown: everything below is from the timed steps
+                      "newton_steps_per_sec_on_sample": sc["newton_steps_per_sec_on_sample"],
+                      "slowdown_sample_to_full": sc["newton_steps_per_sec_on_sample"] / v,
+                      "newton_iters": sc["newton_iters"], "pcg_iters": sc["pcg_iters"], "model_setups": sc["model_setups"],
+                      "pcg_per_newton_sample": sc["pcg_per_newton_sample"], "pcg_per_newton_full": sc["pcg_per_newton_full"],
+                      "element_ratio": sc["element_ratio"], "host_threads": arm.threads},
+           "cpu_baseline": {"value": v, "unit": "Newton-steps/s", "cores": arm.threads, "kind": "port",
+                            "sample": sample_text(n_s, args.n, args.steps, args.warmup, sc, arm.threads)},
            "e2e": {"value": v, "unit": "Newton-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="voxels per edge (default: the 128^3 headline workload)")
-    ap.add_argument("--grains", type=int, default=2000)
+    ap.add_argument("--grains", type=int, default=0, help="grain count (default: BASELINE.json's for the mesh size)")
     ap.add_argument("--krylov-iter", type=int, default=1000)
     ap.add_argument("--true-jacobi", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-same-config", action="store_true", help="skip the sample-mesh GPU runs (N=1 only)")
     ap.add_argument("--nccl-only", action="store_true", help="use NCCL for the CG-loop exchanges instead of the peer-memory kernels")
-    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--ref-n", type=int, default=0, help="sample mesh edge of --impl reference (default: sized to --ref-budget)")
     ap.add_argument("--tuning", action="append", default=[], help="ctas:variant pairs passed to exab200_set_tuning (A/B runs)")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
+    if args.steps < 1 or args.warmup < 0 or args.gpus < 1:
+        raise SystemExit("bench.py: need --steps >= 1, --warmup >= 0, --gpus >= 1")
+    return args
+
+
+def main():
+    args = parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -22,6 +22,14 @@ int orc_num_threads() {
 #endif
 }
 
+// bench.py's CPU legs: launchers such as torch.distributed.run export OMP_NUM_THREADS=1; the baseline must use every
+// host thread it is allowed to, so the count is set explicitly.
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 void orc_hex8_dshape(double* G, double* W) { hex8_dshape(G, W); }
 void orc_voxel_mesh(int nx, int ny, int nz, const double* len, int* e2n, double* coords) {
   voxel_mesh(nx, ny, nz, len[0], len[1], len[2], e2n, coords);
@@ -146,23 +154,12 @@ int orc_model_setup(int xtal, int kin, const double* props, int nprops, const do
   return model_setup(m, ne, dt, temp_k, jac, G, velE, stress0, hist0, stress1, hist1, ddsdde, true);
 }
 
-// Full quasi-static simulation on a voxel mesh.  Returns 0 or the failing step.
-//   bc_* : nbc sets; set s has bc_counts[s] (id, comp, 3 vals) entries, concatenated; comp < 0 = velocity-gradient
-//          BC; bc_vgrads (may be null): 9 per set, row-major L
-//   nr = {rel, abs, iters}, kr = {rel, abs, iters}
-//   auto_time (may be null): {on, dt_start, dt_min, dt_scale, t_final}; then nsteps must be >= ceil(t_final/dt_min)
-//   out_stress nsteps x 6; out_extra nsteps x 16 (may be null); out_iters nsteps x 2 (may be null)
-//   out_stats = {newton_iters, pcg_iters, model_setups, grad_mults, failed_points, seconds, steps taken}
-//   out_dts (may be null): step sizes taken
-int orc_sim_run2(int nx, int ny, int nz, const double* len, int xtal, int kin, const double* props, int nprops,
-                 double temp_k, const int* grain_ids, const double* quats, int ngrains, const double* dts,
-                 int nsteps, int nbc, const int* bc_steps, const int* bc_counts, const int* bc_ids,
-                 const int* bc_comps, const double* bc_vals, const double* bc_vgrads, int assembly, int integ,
-                 int nl_solver, const double* nr, const double* kr, int true_jacobi, const double* opts, int verbose,
-                 const double* auto_time, double* out_stress, double* out_extra, int* out_iters, double* out_stats,
-                 double* out_hist /* final hist0, may be null */, double* out_stress_qp /* final stress0 */,
-                 double* out_dts) {
-  SimConfig c;
+static int make_config(SimConfig& c, int nx, int ny, int nz, const double* len, int xtal, int kin, const double* props, int nprops,
+                       double temp_k, const int* grain_ids, const double* quats, int ngrains, const double* dts,
+                       int nsteps, int nbc, const int* bc_steps, const int* bc_counts, const int* bc_ids,
+                       const int* bc_comps, const double* bc_vals, const double* bc_vgrads, int assembly, int integ,
+                       int nl_solver, const double* nr, const double* kr, int true_jacobi, const double* opts, int verbose,
+                       const double* auto_time) {
   c.nx = nx; c.ny = ny; c.nz = nz;
   for (int i = 0; i < 3; ++i) c.len[i] = len[i];
   c.xtal = xtal; c.kin = kin;
@@ -196,6 +193,30 @@ int orc_sim_run2(int nx, int ny, int nz, const double* len, int xtal, int kin, c
     c.auto_time.dt_scale = auto_time[3]; c.auto_time.t_final = auto_time[4];
     if (nsteps < (int)std::ceil(c.auto_time.t_final / c.auto_time.dt_min)) return -1;
   }
+  return 0;
+}
+
+// Full quasi-static simulation on a voxel mesh.  Returns 0 or the failing step.
+//   bc_* : nbc sets; set s has bc_counts[s] (id, comp, 3 vals) entries, concatenated; comp < 0 = velocity-gradient
+//          BC; bc_vgrads (may be null): 9 per set, row-major L
+//   nr = {rel, abs, iters}, kr = {rel, abs, iters}
+//   auto_time (may be null): {on, dt_start, dt_min, dt_scale, t_final}; then nsteps must be >= ceil(t_final/dt_min)
+//   out_stress nsteps x 6; out_extra nsteps x 16 (may be null); out_iters nsteps x 2 (may be null)
+//   out_stats = {newton_iters, pcg_iters, model_setups, grad_mults, failed_points, seconds, steps taken}
+//   out_dts (may be null): step sizes taken
+int orc_sim_run2(int nx, int ny, int nz, const double* len, int xtal, int kin, const double* props, int nprops,
+                 double temp_k, const int* grain_ids, const double* quats, int ngrains, const double* dts,
+                 int nsteps, int nbc, const int* bc_steps, const int* bc_counts, const int* bc_ids,
+                 const int* bc_comps, const double* bc_vals, const double* bc_vgrads, int assembly, int integ,
+                 int nl_solver, const double* nr, const double* kr, int true_jacobi, const double* opts, int verbose,
+                 const double* auto_time, double* out_stress, double* out_extra, int* out_iters, double* out_stats,
+                 double* out_hist /* final hist0, may be null */, double* out_stress_qp /* final stress0 */,
+                 double* out_dts) {
+  SimConfig c;
+  if (make_config(c, nx, ny, nz, len, xtal, kin, props, nprops, temp_k, grain_ids, quats, ngrains, dts, nsteps, nbc, bc_steps,
+                  bc_counts, bc_ids, bc_comps, bc_vals, bc_vgrads, assembly, integ, nl_solver, nr, kr, true_jacobi, opts, verbose,
+                  auto_time))
+    return -1;
   VoxelSim sim(c);
   auto t0 = std::chrono::steady_clock::now();
   int taken = 0;
@@ -214,5 +235,39 @@ int orc_sim_run2(int nx, int ny, int nz, const double* len, int xtal, int kin, c
   if (out_stress_qp) std::memcpy(out_stress_qp, sim.stress0.data(), sim.stress0.size() * sizeof(double));
   return rc;
 }
+
+// Step-at-a-time driving of the same simulation (bench.py's CPU legs time single steps of it).
+void* orc_sim_create(int nx, int ny, int nz, const double* len, int xtal, int kin, const double* props, int nprops,
+                     double temp_k, const int* grain_ids, const double* quats, int ngrains, int nbc, const int* bc_steps,
+                     const int* bc_counts, const int* bc_ids, const int* bc_comps, const double* bc_vals,
+                     const double* bc_vgrads, int assembly, int integ, int nl_solver, const double* nr, const double* kr,
+                     int true_jacobi, const double* opts, int verbose) {
+  SimConfig c;
+  if (make_config(c, nx, ny, nz, len, xtal, kin, props, nprops, temp_k, grain_ids, quats, ngrains, nullptr, 0, nbc, bc_steps,
+                  bc_counts, bc_ids, bc_comps, bc_vals, bc_vgrads, assembly, integ, nl_solver, nr, kr, true_jacobi, opts, verbose,
+                  nullptr))
+    return nullptr;
+  VoxelSim* sim = new VoxelSim(c);
+  sim->begin();
+  return sim;
+}
+// out[12] = {newton iters, pcg iters, model setups, grad mults (all of this step), seconds, avg stress[6], seconds inside
+// the CG solves}; returns 0 / 1 (Newton failed)
+int orc_sim_step(void* h, double dt, double* out) {
+  VoxelSim* sim = static_cast<VoxelSim*>(h);
+  const SimStats s0 = sim->stats;
+  int iters[2] = {0, 0};
+  auto t0 = std::chrono::steady_clock::now();
+  const int rc = sim->step(dt, &out[5], nullptr, iters, nullptr, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  out[0] = (double)(sim->stats.newton_iters - s0.newton_iters);
+  out[1] = (double)(sim->stats.pcg_iters - s0.pcg_iters);
+  out[2] = (double)(sim->stats.model_setups - s0.model_setups);
+  out[3] = (double)(sim->stats.grad_mults - s0.grad_mults);
+  out[4] = std::chrono::duration<double>(t1 - t0).count();
+  out[11] = sim->stats.pcg_seconds - s0.pcg_seconds;
+  return rc;
+}
+void orc_sim_destroy(void* h) { delete static_cast<VoxelSim*>(h); }
 
 }  // extern "C"

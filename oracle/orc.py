@@ -31,6 +31,7 @@ def lib():
         build()
         _lib = C.CDLL(_LIB)
         _lib.orc_sim_run2.restype = C.c_int
+        _lib.orc_sim_create.restype = C.c_void_p
     return _lib
 
 
@@ -53,6 +54,15 @@ DEFAULT_OPTS = (1.0, 1.0, 1.0, 0.0, 1.0, 1.0)
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def use_all_host_threads():
+    """Launchers (torch.distributed.run) export OMP_NUM_THREADS=1; bench.py's CPU legs must use every host thread
+    this process may run on.  Returns the count now in effect."""
+    n = len(os.sched_getaffinity(0))
+    lib().orc_set_num_threads(n)
+    assert num_threads() == n, (num_threads(), n)
+    return n
 
 
 def hex8_dshape():
@@ -272,3 +282,39 @@ def sim_run(n, length, xtal, kin, props, temp_k, grain_ids, quats, dts, bcs, ass
                            model_setups=int(out_stats[2]), grad_mults=int(out_stats[3]),
                            failed_points=int(out_stats[4]), seconds=float(out_stats[5])),
                 hist=out_hist, stress_qp=out_sq)
+
+
+class SimStepper:
+    """The same simulation as sim_run, driven one time step at a time (bench.py's CPU legs time single steps)."""
+
+    def __init__(self, n, length, xtal, kin, props, temp_k, grain_ids, quats, bcs, assembly=0, integ=0, nl_solver=0,
+                 nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, 1000), true_jacobi=False, opts=DEFAULT_OPTS, verbose=0):
+        nx, ny, nz = n
+        props = _d(props)
+        quats = _d(quats)
+        bc_steps = _i([b[0] for b in bcs])
+        bc_counts = _i([len(b[1]) for b in bcs])
+        bc_ids = _i(np.concatenate([b[1] for b in bcs]))
+        bc_comps = _i(np.concatenate([b[2] for b in bcs]))
+        bc_vals = _d(np.concatenate([np.asarray(b[3], dtype=float).ravel() for b in bcs]))
+        bc_vgrads = _d(np.concatenate([np.asarray(b[4], dtype=float).ravel() if len(b) > 4 else np.zeros(9) for b in bcs]))
+        self._h = C.c_void_p(lib().orc_sim_create(
+            nx, ny, nz, _p(_d(length)), xtal, kin, _p(props), props.size, C.c_double(temp_k), _p(_i(grain_ids)), _p(quats),
+            quats.size // 4, len(bcs), _p(bc_steps), _p(bc_counts), _p(bc_ids), _p(bc_comps), _p(bc_vals), _p(bc_vgrads),
+            assembly, integ, nl_solver, _p(_d(nr)), _p(_d(kr)), int(true_jacobi), _p(_d(opts)), verbose))
+        if not self._h:
+            raise ValueError("orc_sim_create failed")
+
+    def step(self, dt):
+        out = np.zeros(12)
+        rc = lib().orc_sim_step(self._h, C.c_double(dt), _p(out))
+        return dict(rc=rc, newton_iters=int(out[0]), pcg_iters=int(out[1]), model_setups=int(out[2]), grad_mults=int(out[3]),
+                    seconds=float(out[4]), avg_stress=out[5:11].copy(), pcg_seconds=float(out[11]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()

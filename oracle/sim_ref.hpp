@@ -14,6 +14,7 @@
 //   mfem::CGSolver (external; restated from MFEM's published algorithm)
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -65,6 +66,7 @@ struct SimConfig {
 struct SimStats {
   long newton_iters = 0, pcg_iters = 0, model_setups = 0, grad_mults = 0;
   int failed_points = 0;
+  double pcg_seconds = 0.0;  // wall time inside pcg() (bench.py's CPU legs split a step into its CG and non-CG parts)
 };
 
 // ExaCMechModel::ModelSetup for one batch of elements: begin->end copies, grad_calc,
@@ -289,7 +291,10 @@ class VoxelSim {
   // NonlinearMechOperator::Setup<upd_crds> (src/mechanics_operator.cpp:311-348)
   void setup(const dvec& k, bool upd_crds) {
     if (upd_crds)
-      for (long i = 0; i < ndof; ++i) x_end[i] = k[i] * dt + x_beg[i];
+      {
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < ndof; ++i) x_end[i] = k[i] * dt + x_beg[i];
+      }
     dvec xE(ne * 24);
     gather(ne, nn, e2n.data(), x_end.data(), xE.data());
     jacobians(ne, G.data(), xE.data(), jac.data());
@@ -371,10 +376,19 @@ class VoxelSim {
   // mfem::CGSolver::Mult with the MechOperatorJacobiSmoother as preconditioner,
   // iterative_mode = false (src/mechanics_solver.cpp:72, src/mechanics_operator_ext.cpp:37-55)
   int pcg(const dvec& b, dvec& x) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int it = pcg_body(b, x);
+    stats.pcg_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return it;
+  }
+  int pcg_body(const dvec& b, dvec& x) {
     const long n = ndof;
     dvec r(b), z(n), d(n);
     std::fill(x.begin(), x.end(), 0.0);
-    auto prec = [&](const dvec& in, dvec& out) { for (long i = 0; i < n; ++i) out[i] = dinv[i] * in[i]; };
+    auto prec = [&](const dvec& in, dvec& out) {
+#pragma omp parallel for schedule(static)
+      for (long i = 0; i < n; ++i) out[i] = dinv[i] * in[i];
+    };
     prec(r, z);
     d = z;
     double nom = dot(d, r);
@@ -388,12 +402,14 @@ class VoxelSim {
     int i = 1;
     for (;;) {
       const double alpha = nom / den;
+#pragma omp parallel for schedule(static)
       for (long j = 0; j < n; ++j) { x[j] += alpha * d[j]; r[j] -= alpha * z[j]; }
       prec(r, z);
       const double betanom = dot(r, z);
       if (betanom <= r0) break;
       if (++i > cfg.kr_iter) break;
       const double beta = betanom / nom;
+#pragma omp parallel for schedule(static)
       for (long j = 0; j < n; ++j) d[j] = z[j] + beta * d[j];
       grad_mult(d, z);
       den = dot(d, z);
@@ -474,13 +490,44 @@ class VoxelSim {
   // sizes actually taken, *out_nsteps their number.
   int run(double* avg_stress, double* extra /* nsteps x 16 or null */, int* iters /* nsteps x 2 or null */,
           double* out_dts = nullptr, int* out_nsteps = nullptr) {
-    dvec v(ndof, 0.0), vprev(ndof, 0.0);
     const AutoTime& at = cfg.auto_time;
     const int nsteps = at.on ? (int)std::ceil(at.t_final / at.dt_min) : (int)cfg.dts.size();
-    double t = 0.0, dt_class = at.dt_start;
+    begin();
     if (out_nsteps) *out_nsteps = 0;
     for (int ti = 1; ti <= nsteps; ++ti) {
-      dt = at.on ? std::min(dt_class, at.t_final - t) : cfg.dts[ti - 1];
+      bool last_step = false;
+      const int rc = step(at.on ? 0.0 : cfg.dts[ti - 1], &avg_stress[(ti - 1) * 6], extra ? &extra[(ti - 1) * 16] : nullptr,
+                          iters ? &iters[(ti - 1) * 2] : nullptr, out_dts ? &out_dts[ti - 1] : nullptr, &last_step);
+      if (rc) return ti;
+      if (out_nsteps) *out_nsteps = ti;
+      if (last_step) break;
+    }
+    return 0;
+  }
+
+  // time-loop state for step-at-a-time driving (run() above, and the bench's CPU-baseline leg, which times single steps)
+  dvec v_cur, v_prev;
+  double t_now = 0.0, dt_class = 0.0;
+  int ti_now = 0;
+  void begin() {
+    v_cur.assign(ndof, 0.0);
+    v_prev.assign(ndof, 0.0);
+    t_now = 0.0;
+    dt_class = cfg.auto_time.dt_start;
+    ti_now = 0;
+  }
+
+  // one pass of the time loop (src/mechanics_driver.cpp:837-907); dt_fixed is ignored with Time.Auto.  Returns 0, or 1 if
+  // the Newton solve failed.
+  int step(double dt_fixed, double* avg_stress /*6*/, double* ex /*16 or null*/, int* iters /*2 or null*/,
+           double* out_dt /*or null*/, bool* last /*or null*/) {
+    dvec& v = v_cur;
+    dvec& vprev = v_prev;
+    const AutoTime& at = cfg.auto_time;
+    double& t = t_now;
+    const int ti = ++ti_now;
+    {
+      dt = at.on ? std::min(dt_class, at.t_final - t) : dt_fixed;
       t += dt;
       bool last_step = at.on && std::fabs(t - at.t_final) <= std::fabs(1e-3 * dt);
       const long pcg0 = stats.pcg_iters;
@@ -512,23 +559,21 @@ class VoxelSim {
           last_step = std::fabs(t - at.t_final) <= std::fabs(1e-3 * dt);
         }
         const double factor = ((double)cfg.nr_iter * at.dt_scale) / (double)nit;
-        if (out_dts) out_dts[ti - 1] = dt;
+        if (out_dt) *out_dt = dt;
         dt_class *= factor;
         if (dt_class < at.dt_min) dt_class = at.dt_min;
       } else {
         ok = newton(v, &nit);
-        if (out_dts) out_dts[ti - 1] = dt;
+        if (out_dt) *out_dt = dt;
       }
       if (cfg.verbose) std::printf("step %d: t %.6f dt %.6f newton its %d converged %d\n", ti, t, dt, nit, (int)ok);
-      if (!ok) return ti;
-      if (out_nsteps) *out_nsteps = ti;
+      if (!ok) return 1;
       // UpdateModel: swap begin/end, then averages over the end-of-step (current) mesh
       stress0.swap(stress1);
       hist0.swap(hist1);
       x_beg = x_end;
-      vol_avg(stress0, 6, &avg_stress[(ti - 1) * 6], true);
-      if (extra) {
-        double* ex = &extra[(ti - 1) * 16];
+      vol_avg(stress0, 6, avg_stress, true);
+      if (ex) {
         dvec tmp(mat.nhist);
         vol_avg(hist0, mat.nhist, tmp.data(), false);
         ex[0] = tmp[ecm::iHistA_flowStr];
@@ -561,8 +606,8 @@ class VoxelSim {
           vol_avg(F, 9, &ex[7], true);
         }
       }
-      if (iters) { iters[(ti - 1) * 2] = nit; iters[(ti - 1) * 2 + 1] = (int)(stats.pcg_iters - pcg0); }
-      if (last_step) break;
+      if (iters) { iters[0] = nit; iters[1] = (int)(stats.pcg_iters - pcg0); }
+      if (last) *last = last_step;
     }
     return 0;
   }
