@@ -24,6 +24,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ecm {
@@ -193,6 +195,15 @@ struct Options {
   double av_power = 0.0;        // a_V^power factor on the elastic-strain-rate terms (0 = none)
   bool eos_mu_form = true;      // p = K (1/V - 1) instead of K (1 - V)
   bool wp_elastic_terms = true; // second-order (e D^p - D^p e), skew(edot e) terms in the spin eq.
+  double knob[6] = {0, 0, 0, 0, 0, 0};  // EXPERIMENT knobs (env ORC_KNOB0..5), all 0 in normal operation
+  Options() {
+    for (int i = 0; i < 6; ++i) {
+      char nm[16];
+      std::snprintf(nm, sizeof nm, "ORC_KNOB%d", i);
+      const char* e = std::getenv(nm);
+      if (e) knob[i] = std::atof(e);
+    }
+  }
 };
 
 struct Material {
@@ -601,7 +612,7 @@ struct UpdateProblem {
     for (int k = 0; k < 3; ++k) {
       double xe_dp = 0.0, xedot_e = 0.0;
       for (int i = 0; i < 5; ++i) { xe_dp += 0.5 * Me[i][k] * dp[i]; xedot_e += 0.5 * Medot[i][k] * e_f[i]; }
-      R[5 + k] = rotincr_scale_inv * dt * (xi[k] * dt_ri + wp[k] - w_lat[k] + c2 * (xe_dp - 0.5 * xedot_e));
+      R[5 + k] = rotincr_scale_inv * dt * (xi[k] * dt_ri + (1.0 + m.opt.knob[0]) * wp[k] - (1.0 + m.opt.knob[1]) * w_lat[k] + c2 * (xe_dp - 0.5 * xedot_e));
     }
     if (!Jac) return;
     // d gdot / d e_f
