@@ -76,7 +76,8 @@ static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((ne
 template <int EPT, int STAGES, int MODE, bool ESS>
 static int launch_gm(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st) {
   using SM = GradMultSmem<EPT, STAGES>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device (context), not per process
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_grad_mult_pa<EPT, STAGES, MODE, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
     attr_set = true;
@@ -92,7 +93,8 @@ static int launch_gm(exab200_ctx* c, const double* x, double* y, ElemIO io, cuda
 template <int NW, int STAGES, int MODE, bool ESS, bool JX = false>
 static int launch_gmw(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
   constexpr int smem = NW * STAGES * (JX ? kWarpStageBytesJX : kWarpStageBytes) + NW * STAGES * 8;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device (context), not per process
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_grad_mult_pa_w<NW, STAGES, MODE, ESS, JX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -151,7 +153,8 @@ static int encode_tangent_map(exab200_ctx* c) {
 template <int NW, int STAGES, bool ESS>
 static int launch_gmc(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
   constexpr int smem = NW * STAGES * kWarpStageBytesC + NW * STAGES * 8 + 1024;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device (context), not per process
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_grad_mult_pa_c<NW, STAGES, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -178,7 +181,8 @@ static int launch_grad_mult_compact(exab200_ctx* c, const double* x, double* y, 
 template <int NW, int STAGES, bool ESS>
 static int launch_eap(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot, int ctas) {
   constexpr int smem = NW * STAGES * kEaStageBytes + NW * STAGES * 8;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device (context), not per process
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_ea_mult_p<NW, STAGES, ESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(256) k_grad_calc(const double* __restrict__ ja
 template <int NSLIP, int KIN, int MODE, int MINB>
 static int launch_k1(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0, const double* h0,
                      double* s1, double* h1, double* mg, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device (context), not per process
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
   if (!attr_set) {
     CK(cudaFuncSetAttribute(k_model_setup<NSLIP, KIN, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
     attr_set = true;

@@ -335,7 +335,11 @@ struct KernelTimer {
 // 16 block counter, 17 error;  [64,192) scalar slots [par][rank][8];  [192, 192+12*plane) halo slots
 // [from-lo | from-hi][par][3*plane].
 constexpr int kMbScal = 64, kMbHalo = 192;
-constexpr long long kSpinLimit = 4000000000LL;  // ~2 s: turn a lost peer into an error instead of a hang
+// A lost peer becomes an error instead of a hang: after the limit (clock64 ticks, ~10 s by default;
+// EXAHOST_SPIN_LIMIT_S overrides) the waiter raises the mailbox error flag AND poisons what it was about to
+// produce with NaN, so that the CG scalars turn non-finite and the host loop stops at its next stopping test
+// instead of iterating on stale data (the flag is then reported as the cause).
+__device__ long long g_spin_limit = 20000000000LL;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -348,7 +352,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq, double* mb) {
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < seq) {
-    if (clock64() - t0 > kSpinLimit) { reinterpret_cast<unsigned long long*>(mb)[17] = 1ull; return false; }
+    if (clock64() - t0 > g_spin_limit) { reinterpret_cast<unsigned long long*>(mb)[17] = 1ull; return false; }
   }
   return true;
 }
@@ -371,13 +375,14 @@ __device__ __forceinline__ void warp_allreduce_p2p(double* val, const PeerTable&
     for (int k = 0; k < n; ++k) dst[k] = val[k];
     __threadfence_system();
     st_release_sys(reinterpret_cast<unsigned long long*>(peers.p[lane]) + 8 + rank, seq);
-    spin_until(reinterpret_cast<unsigned long long*>(mb) + 8 + lane, seq, mb);
   }
+  const bool ok = (lane < nranks) ? spin_until(reinterpret_cast<unsigned long long*>(mb) + 8 + lane, seq, mb) : true;
+  const bool all_ok = __all_sync(0xffffffffu, ok);
   __syncwarp();
   if (lane < n) {
     double s = 0.0;
     for (int r = 0; r < nranks; ++r) s += ld_cg(&mb[kMbScal + (par * 8 + r) * 8 + lane]);
-    val[lane] = s;
+    val[lane] = all_ok ? s : __longlong_as_double(0x7ff8000000000000LL);
   }
 }
 
@@ -393,6 +398,7 @@ __global__ void __launch_bounds__(256) k_halo_p2p(double* __restrict__ v, double
   }
   const int par = (int)(seq & 1);
   const long n3 = 3 * plane, top = nn - plane;
+  __shared__ bool s_ok;
   // push: my bottom plane -> lower neighbour's "from-hi" slot, my top plane -> upper neighbour's "from-lo" slot
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)nblk * blockDim.x) {
     const long c = i / plane, n = i - c * plane;
@@ -410,14 +416,17 @@ __global__ void __launch_bounds__(256) k_halo_p2p(double* __restrict__ v, double
       if (lo) st_release_sys(reinterpret_cast<unsigned long long*>(lo) + 1, seq);  // I am the lower one's "hi"
       if (hi) st_release_sys(reinterpret_cast<unsigned long long*>(hi) + 0, seq);  // I am the upper one's "lo"
     }
-    if (lo) spin_until(&flags[0], seq, mb);
-    if (hi) spin_until(&flags[1], seq, mb);
+    bool ok = true;
+    if (lo) ok = spin_until(&flags[0], seq, mb) && ok;
+    if (hi) ok = spin_until(&flags[1], seq, mb) && ok;
+    s_ok = ok;
   }
   __syncthreads();
+  const double poison = s_ok ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)nblk * blockDim.x) {
     const long c = i / plane, n = i - c * plane;
-    if (lo) v[c * nn + n] += ld_cg(&mb[kMbHalo + (0 + par) * n3 + i]);
-    if (hi) v[c * nn + top + n] += ld_cg(&mb[kMbHalo + (2 + par) * n3 + i]);
+    if (lo) v[c * nn + n] += ld_cg(&mb[kMbHalo + (0 + par) * n3 + i]) + poison;
+    if (hi) v[c * nn + top + n] += ld_cg(&mb[kMbHalo + (2 + par) * n3 + i]) + poison;
   }
 }
 
@@ -520,7 +529,13 @@ class SlabComm {
   std::vector<void*> opened;
 
   void Init(int rank_, int nranks_, const void* nccl_id, cudaStream_t s, long nn_, long plane_) {
+    if (nranks_ < 1 || nranks_ > 8 || rank_ < 0 || rank_ >= nranks_)
+      throw Abort{"SlabComm: 1 <= nranks <= 8 (one box of NVLink peers: PeerTable and the mailbox layout hold 8 ranks) and 0 <= rank < nranks"};
     rank = rank_; nranks = nranks_; stream = s; nn = nn_; plane = plane_;
+    if (const char* e = std::getenv("EXAHOST_SPIN_LIMIT_S")) {
+      const long long ticks = (long long)(std::atof(e) * 2.0e9);
+      if (ticks > 0) HCK(cudaMemcpyToSymbol(g_spin_limit, &ticks, sizeof(ticks)));
+    }
     n_owned = (rank == nranks - 1) ? nn : nn - plane;
     partial.SetSize(kRedBlocks);
     scal.SetSize(8);
@@ -732,6 +747,7 @@ class NonlinearMechOperator : public Operator {
   mutable GradientOperator jacobian;
   Vector ess_mask_dev;           // device copy of the per-node essential mask (bytes)
   mutable long grad_mults = 0, residuals = 0;
+  bool need_diag = false;        // set when the smoother refreshes its inverse diagonal (true_jacobi)
   mutable KernelTimer tm_grad_mult, tm_model_setup;
 
   NonlinearMechOperator(exab200_ctx* c, SlabComm* cm, cudaStream_t s, ExaModel* m, long ne, long nn, Vector* xb)
@@ -758,7 +774,9 @@ class NonlinearMechOperator : public Operator {
   // src/mechanics_operator.cpp:436-443
   Operator& GetGradient(const Vector&) const {
     XCK(exab200_grad_setup(ctx, model->dt, model->matGrad->Read(), el_jac.Read(), stream));
-    jacobian.AssembleDiagonal(diag);
+    // The reference assembles the diagonal here on every call (src/mechanics_operator.cpp:441) although its smoother
+    // never picks it up; nothing reads `diag` unless the real Jacobi smoother is on.
+    if (need_diag) jacobian.AssembleDiagonal(diag);
     return jacobian;
   }
   // src/mechanics_operator.cpp:446-483
@@ -911,6 +929,9 @@ class CGSolver {
       }
       HCK(cudaEventSynchronize(ev[slot]));
       const double betanom = h_bet[slot];
+      // mfem::CGSolver leaves the loop on betanom < 0 and on a non-positive denominator; a NaN (den == 0, or a
+      // peer-memory exchange that timed out and poisoned its result) must not run max_iter applies on garbage
+      if (!std::isfinite(betanom) || betanom < 0.0) { converged = 0; final_iter = i; break; }
       if (betanom <= r0) { converged = 1; final_iter = i; break; }
       if (++i > max_iter) break;
     }
@@ -944,7 +965,10 @@ class ExaNewtonSolver {
     double scale = 1.0;
     int it;
     for (it = 0; true; ++it) {
-      if (!std::isfinite(norm)) throw Abort{"Newton: residual norm is not finite"};
+      if (!std::isfinite(norm)) {
+        if (comm->PeerError()) throw Abort{"peer-memory collective timed out waiting for a neighbour"};
+        throw Abort{"Newton: residual norm is not finite"};
+      }
       if (print_level >= 0 && comm->rank == 0) {
         std::printf("Newton iteration %2d : ||r|| = %g", it, norm);
         if (it > 0) std::printf(", ||r||/||r_0|| = %g", norm / norm0);
@@ -1171,6 +1195,7 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
     s->newton->oper_mech = s->oper.get();
     s->newton->prec = s->cg.get();
     s->newton->smoother = s->smoother.get();
+    s->oper->need_diag = s->smoother->refresh;
     s->newton->print_level = cfg->verbose ? 0 : -1;
     HCK(cudaMallocHost(&s->h_pinned, sizeof(double) * n));
     for (int i = 0; i < 4; ++i) HCK(cudaEventCreate(&s->ev[i]));
@@ -1287,11 +1312,19 @@ static int step_impl(exahost_sim* s, double dt, int bc_changed, const double* h_
       s->newton->Mult(s->v_sol);
       newton_iters = s->newton->final_iter;
     }
-    if (!s->newton->converged) throw Abort{"Newton Solver did not converge."};  // MFEM_VERIFY, src/system_driver.cpp:287
+    // Failures are made collective before anyone throws: the Newton verdict rests on all-reduced norms (identical on
+    // every rank), the failed-point count and the peer-timeout flag are summed over the ranks here, so either every
+    // rank aborts or none does (a rank that throws alone would leave its neighbours spinning in the next exchange).
     int nfail = 0;
     XCK(exab200_failed_points(s->ctx, s->stream, &nfail));
-    if (nfail) throw Abort{"material update failed at " + std::to_string(nfail) + " quadrature points"};
-    if (s->comm.PeerError()) throw Abort{"peer-memory collective timed out waiting for a neighbour"};
+    double fl[2] = {(double)nfail, s->comm.PeerError() ? 1.0 : 0.0};
+    if (s->comm.nranks > 1 && fl[1] == 0.0 && std::isfinite(s->newton->final_norm)) {
+      HCK(cudaMemcpyAsync(s->sums.d, fl, sizeof(fl), cudaMemcpyHostToDevice, s->stream));
+      s->comm.AllReduceFetch(s->sums.d, 2, fl);
+    }
+    if (fl[1] != 0.0 || s->comm.PeerError()) throw Abort{"peer-memory collective timed out waiting for a neighbour"};
+    if (!s->newton->converged) throw Abort{"Newton Solver did not converge."};  // MFEM_VERIFY, src/system_driver.cpp:287
+    if (fl[0] != 0.0) throw Abort{"material update failed at " + std::to_string((long)fl[0]) + " quadrature points (all ranks)"};
     double avg[6];
     s->UpdateModel(avg);
     // x_beg = x_cur (src/mechanics_driver.cpp:907): x_beg += dt * v

@@ -621,37 +621,32 @@ EXAB_UNROLL_SLIP
     // plastic dissipation rate sum_a tau_a gdot_a = T . D^p
     disRate = T[0] * dp[0] + T[1] * dp[1] + T[2] * dp[2] + T[3] * dp[3] + T[4] * dp[4];
 
+    // Strain-rate and spin equations.  The plastic velocity gradient acts in the unstretched lattice (no [e, W^p] /
+    // [e, D^p] terms: what the reference's goldens pin, see oracle/ecmech_port.hpp Options::slip_stretch_terms); the
+    // spin equation keeps the skew part of edot e.
     double Me[5][3], Medot[5][3];
     comm_Me(e_f, Me);
     comm_Me(edot, Medot);
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const double ewp = Me[i][0] * wp[0] + Me[i][1] * wp[1] + Me[i][2] * wp[2];
-      R[i] = eps_si * (edot[i] + ewp + dp[i] - d_lat[i]);
-    }
+    for (int i = 0; i < 5; ++i) R[i] = eps_si * (edot[i] + dp[i] - d_lat[i]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      double xe_dp = 0.0, xedot_e = 0.0;
+      double xedot_e = 0.0;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) { xe_dp += 0.5 * Me[i][k] * dp[i]; xedot_e += 0.5 * Medot[i][k] * e_f[i]; }
-      R[5 + k] = rot_si * dt * (xi[k] * dt_ri + wp[k] - w_lat[k] + (xe_dp - 0.5 * xedot_e));
+      for (int i = 0; i < 5; ++i) xedot_e += 0.5 * Medot[i][k] * e_f[i];
+      R[5 + k] = rot_si * dt * (xi[k] * dt_ri + wp[k] - w_lat[k] - 0.5 * xedot_e);
     }
     if (!want_jac) return;
     // dDp(i,j) = S(i,j) K_j ; dWp(k,j) = Wq(k,j) K_j
-    double Mwp[5][5], JrM[3][3], Mdl[5][3], Mdp[5][3];
-    comm_Mw(wp, Mwp);
+    double JrM[3][3], Mdl[5][3];
     exp_Jr(xi, th2, th, sh, ch, JrM);
     comm_Me(d_lat, Mdl);
-    comm_Me(dp, Mdp);
     const double ce = eps_si * e_scale, cr = eps_si * r_scale;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        double v = S[sidx_sym(i, j)];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) v += Me[i][k] * Wq[k * 5 + j];
-        v = v * m.Kdiag[j] + (i == j ? dt_ri : 0.0) + Mwp[i][j];
+        const double v = S[sidx_sym(i, j)] * m.Kdiag[j] + (i == j ? dt_ri : 0.0);
         J[EXAB_JIDX(i, j)] = ce * v;
       }
 #pragma unroll
@@ -668,10 +663,7 @@ EXAB_UNROLL_SLIP
     for (int k = 0; k < 3; ++k) {
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        double t = Wq[k * 5 + j];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) t += 0.5 * Me[i][k] * S[sidx_sym(i, j)];
-        t = t * m.Kdiag[j] - 0.5 * Mdp[j][k] - 0.5 * (-0.5 * Me[j][k] * dt_ri + 0.5 * Medot[j][k]);
+        const double t = Wq[k * 5 + j] * m.Kdiag[j] - 0.5 * (-0.5 * Me[j][k] * dt_ri + 0.5 * Medot[j][k]);
         J[EXAB_JIDX(5 + k, j)] = rde * t;
       }
 #pragma unroll
@@ -921,7 +913,7 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
   h1[iH_shrEff] = h0[iH_shrEff] + prob.shrate * dt;
   {
     double flow = prob.gv(0);
-    if (dEff > idp_tiny_sqrt) flow = prob.disRate / dEff;
+    if (dEff > idp_tiny_sqrt) flow = prob.disRate * prob.detVi / dEff;  // Cauchy stress : D^p (per current volume)
     const double plw = (dEff > idp_tiny_sqrt) ? flow * dEff * dt : 0.0;  // kernel_postprocessing :135-140
     h1[iH_flowStr] = plw + h0[iH_flowStr];
   }

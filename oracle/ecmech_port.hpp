@@ -24,8 +24,6 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
-#include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 namespace ecm {
@@ -194,16 +192,12 @@ struct Options {
   bool hard_lag = true;         // hardness advanced with beginning-of-step slip rates
   double av_power = 0.0;        // a_V^power factor on the elastic-strain-rate terms (0 = none)
   bool eos_mu_form = true;      // p = K (1/V - 1) instead of K (1 - V)
-  bool wp_elastic_terms = true; // second-order (e D^p - D^p e), skew(edot e) terms in the spin eq.
-  double knob[6] = {0, 0, 0, 0, 0, 0};  // EXPERIMENT knobs (env ORC_KNOB0..5), all 0 in normal operation
-  Options() {
-    for (int i = 0; i < 6; ++i) {
-      char nm[16];
-      std::snprintf(nm, sizeof nm, "ORC_KNOB%d", i);
-      const char* e = std::getenv(nm);
-      if (e) knob[i] = std::atof(e);
-    }
-  }
+  // First-order effect of the elastic stretch on the slip kinematics: the [e, W^p] term of the strain-rate equation
+  // and the [e, D^p] term of the spin equation that a consistent expansion of V L^p V^-1 produces.  ExaCMech does NOT
+  // carry them (its plastic velocity gradient acts in the unstretched lattice): with them the reference's voce_*
+  // goldens are missed by 1e-5 of the axial stress in the shear components, without them every printed value is
+  // reproduced to about one unit of its 6th digit (tests/test_oracle_goldens.py).
+  bool slip_stretch_terms = false;
 };
 
 struct Material {
@@ -601,18 +595,18 @@ struct UpdateProblem {
     double Me[5][3];
     cm.Me(e_f, Me);
     const double av = std::pow(a_V_ri, -m.opt.av_power);
-    const double c2 = m.opt.wp_elastic_terms ? 1.0 : 0.0;
+    const double c2 = m.opt.slip_stretch_terms ? 1.0 : 0.0;
     // X(a,b)[k] = 0.5 * sum_i Me(a)[i][k] b[i] = axial(a b - b a)
     double Medot[5][3];
     cm.Me(edot, Medot);
     for (int i = 0; i < 5; ++i) {
-      const double ewp = Me[i][0] * wp[0] + Me[i][1] * wp[1] + Me[i][2] * wp[2];
+      const double ewp = c2 * (Me[i][0] * wp[0] + Me[i][1] * wp[1] + Me[i][2] * wp[2]);
       R[i] = epsdot_scale_inv * (av * (edot[i] + ewp) + dp[i] - d_lat[i]);
     }
     for (int k = 0; k < 3; ++k) {
       double xe_dp = 0.0, xedot_e = 0.0;
       for (int i = 0; i < 5; ++i) { xe_dp += 0.5 * Me[i][k] * dp[i]; xedot_e += 0.5 * Medot[i][k] * e_f[i]; }
-      R[5 + k] = rotincr_scale_inv * dt * (xi[k] * dt_ri + (1.0 + m.opt.knob[0]) * wp[k] - (1.0 + m.opt.knob[1]) * w_lat[k] + c2 * (xe_dp - 0.5 * xedot_e));
+      R[5 + k] = rotincr_scale_inv * dt * (xi[k] * dt_ri + wp[k] - w_lat[k] + c2 * xe_dp - 0.5 * xedot_e);
     }
     if (!Jac) return;
     // d gdot / d e_f
@@ -632,8 +626,8 @@ struct UpdateProblem {
     for (int x8 = 0; x8 < 64; ++x8) Jac[x8] = 0.0;
     for (int i = 0; i < 5; ++i) {
       for (int j = 0; j < 5; ++j) {
-        double v = av * ((i == j ? dt_ri : 0.0) + Mwp[i][j]) + dDp_de[i][j];
-        for (int k = 0; k < 3; ++k) v += av * Me[i][k] * dWp_de[k][j];
+        double v = av * ((i == j ? dt_ri : 0.0) + c2 * Mwp[i][j]) + dDp_de[i][j];
+        for (int k = 0; k < 3; ++k) v += c2 * av * Me[i][k] * dWp_de[k][j];
         Jac[i * 8 + j] = epsdot_scale_inv * v * e_scale;
       }
       for (int k = 0; k < 3; ++k) {
@@ -653,11 +647,11 @@ struct UpdateProblem {
           // X(e,dp): d/de_j -> -0.5*Mdp[j][k] (antisymmetry) ... plus through dp
           double t = -0.5 * Mdp[j][k];
           for (int i = 0; i < 5; ++i) t += 0.5 * Me[i][k] * dDp_de[i][j];
-          // -0.5 X(edot,e): d/de_j = -0.5*( X(e_j/dt, e) + X(edot, e_j) )
-          //   X(e_j, e)[k] = -0.5*Me(e)[j][k];  X(edot, e_j)[k] = 0.5*Medot[j][k]
-          t += -0.5 * (-0.5 * Me[j][k] * dt_ri + 0.5 * Medot[j][k]);
           v += c2 * t;
         }
+        // -0.5 X(edot,e): d/de_j = -0.5*( X(e_j/dt, e) + X(edot, e_j) )
+        //   X(e_j, e)[k] = -0.5*Me(e)[j][k];  X(edot, e_j)[k] = 0.5*Medot[j][k]
+        v += -0.5 * (-0.5 * Me[j][k] * dt_ri + 0.5 * Medot[j][k]);
         Jac[(5 + k) * 8 + j] = rotincr_scale_inv * dt * v * e_scale;
       }
       for (int l = 0; l < 3; ++l) {
@@ -831,7 +825,10 @@ inline int get_response_sngl(const Material& m, double dt, const double* d_svec_
   {
     const double dEff = vecd_Deff(prob.d_sm);
     double flow = prob.kv.g[0];
-    if (dEff > idp_tiny_sqrt) flow = disRate / dEff;
+    // dissipation per CURRENT volume (Cauchy stress : D^p = Kirchhoff resolved shear stresses . slip rates / det V): what the
+    // reference's voce_ea_pl_work.txt / voce_ea_cs_pl_work.txt pin (with the Kirchhoff value the integrated plastic work
+    // is high by the elastic volume strain, 1.0e-4 ... 1.7e-4 relative; with this one it matches to the printed digits)
+    if (dEff > idp_tiny_sqrt) flow = disRate * prob.detVi / dEff;
     hist[iHistA_flowStr] = flow;
   }
   hist[iHistA_nFEval] = (double)nfev;

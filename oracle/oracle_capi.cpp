@@ -88,7 +88,7 @@ static void set_opts(ecm::Options& o, const double* opts) {
   o.eos_temperature = opts[1] != 0.0;
   o.hard_lag = opts[2] != 0.0;
   o.av_power = opts[3];
-  o.wp_elastic_terms = opts[4] != 0.0;
+  o.slip_stretch_terms = opts[4] != 0.0;
   o.eos_mu_form = opts[5] != 0.0;
 }
 

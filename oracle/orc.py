@@ -49,7 +49,8 @@ def _i(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-DEFAULT_OPTS = (1.0, 1.0, 1.0, 0.0, 1.0, 1.0)
+# (kirchhoff_rss, eos_temperature, hard_lag, av_power, slip_stretch_terms, eos_mu_form): see ecm::Options
+DEFAULT_OPTS = (1.0, 1.0, 1.0, 0.0, 0.0, 1.0)
 
 
 def num_threads():

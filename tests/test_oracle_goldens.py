@@ -1,13 +1,20 @@
 """The oracle pinned against the reference's own golden outputs (test/data/*_stress.txt, checked by
-test/test_mechanics.py:11-31,49-54).  The goldens print 6 significant digits; the oracle reproduces
-the loaded (zz) component to <= 1.5e-5 relative and every component to <= 1.5e-5 of the loaded one
-over the whole history ('Oracle parity status')."""
+test/test_mechanics.py:11-31,49-54).  The goldens print 6 significant digits.
+
+Status ('Oracle and parity status'):
+  * FCC/BCC Voce and Voce-NL under monotonic loading (voce_pa, voce_ea, voce_full, voce_nl_full, voce_bcc, voce_ea_cs):
+    every printed axial stress is reproduced to within ONE unit of its 6th digit (<= 1.4e-6 relative) and every other
+    component to <= 2e-8 of the axial stress -- i.e. to the print resolution; the reference's own criterion
+    (identical printed digits) is missed only by last-digit rounding flips.
+  * KMBalD (mtsdd_bcc, mtsdd_full): 1.4e-5 / 7.5e-6 of the peak axial stress (transition regime), shear 8e-8.
+  * load reversals (voce_full_cyclic*): 2.2e-5 of the peak stress (the elastic unloading branch).
+"""
+import math
+
 import numpy as np
 import pytest
 
 import refcases
-
-TOL = 1.5e-5
 
 
 def _run(orc, name, nsteps):
@@ -19,25 +26,69 @@ def _run(orc, name, nsteps):
     return r, gold[:nsteps]
 
 
-def _check(r, gold):
-    s = r["stress"]
-    scale = np.abs(gold[:, 2:3])
-    err = np.abs(s - gold) / scale
-    assert err.max() < TOL, err.max()
+def _ulp6(v):
+    """one unit of the 6th significant digit of a printed value"""
+    return 10.0 ** (math.floor(math.log10(abs(v))) - 5)
 
 
-def test_voce_pa_full_history(orc):
-    r, gold = _run(orc, "voce_pa", 40)
-    _check(r, gold)
-    # iteration counts are part of the parity record (reference = identity-preconditioned CG)
-    assert r["stats"]["newton_iters"] < 120
+def golden_errors(s, gold):
+    """(largest axial error in units of the golden's last printed digit, largest axial error / peak axial stress,
+    largest shear-component error / peak, largest lateral-component error / peak)"""
+    peak = np.abs(gold[:, 2]).max()
+    zz_ulp = max(abs(s[i, 2] - gold[i, 2]) / _ulp6(gold[i, 2]) for i in range(len(gold)))
+    return (zz_ulp, np.abs(s[:, 2] - gold[:, 2]).max() / peak, np.abs(s[:, 3:] - gold[:, 3:]).max() / peak,
+            np.abs(s[:, :2] - gold[:, :2]).max() / peak)
 
 
-@pytest.mark.parametrize("name,nsteps", [("voce_ea", 8), ("voce_full", 8), ("voce_bcc", 8), ("voce_nl_full", 6), ("mtsdd_bcc", 10),
-                                         ("mtsdd_full", 10)])
-def test_other_cases_prefix(orc, name, nsteps):
+# per case: steps run in the default suite, and the bounds (axial in last-digit units or None, axial / peak, shear / peak)
+VOCE = dict(zz_ulp=1.25, zz=3.0e-6, shear=6.0e-8)
+KMBALD = dict(zz_ulp=None, zz=1.6e-5, shear=1.5e-7)
+CASES = [("voce_pa", 40, VOCE), ("voce_ea", 8, VOCE), ("voce_full", 8, VOCE), ("voce_nl_full", 6, VOCE), ("voce_bcc", 40, VOCE),
+         ("voce_ea_cs", 40, VOCE), ("mtsdd_bcc", 40, KMBALD), ("mtsdd_full", 40, KMBALD)]
+
+
+def _check(r, gold, lim):
+    zz_ulp, zz, shear, lat = golden_errors(r["stress"], gold)
+    if lim["zz_ulp"] is not None:
+        assert zz_ulp <= lim["zz_ulp"], zz_ulp
+    assert zz <= lim["zz"], zz
+    assert shear <= lim["shear"], shear
+    assert lat <= 1.5e-8, lat
+
+
+@pytest.mark.parametrize("name,nsteps,lim", CASES, ids=[c[0] for c in CASES])
+def test_monotonic_goldens(orc, name, nsteps, lim):
     r, gold = _run(orc, name, nsteps)
-    _check(r, gold)
+    _check(r, gold, lim)
+    if name == "voce_pa":
+        # iteration counts are part of the parity record (reference = identity-preconditioned CG)
+        assert r["stats"]["newton_iters"] < 120
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name,lim", [("voce_ea", VOCE), ("voce_full", VOCE), ("voce_nl_full", VOCE)], ids=["voce_ea", "voce_full", "voce_nl_full"])
+def test_monotonic_goldens_whole_history(orc, name, lim):
+    """the remaining 40-row histories (same material point physics as voce_pa through other operator paths)"""
+    r, gold = _run(orc, name, 40)
+    _check(r, gold, lim)
+
+
+def test_printed_digits_of_voce_pa(orc):
+    """The reference's criterion is identical 6-digit prints (test/test_mechanics.py:11-31).  Count how far we are:
+    no printed value may be off by more than one unit of its last digit (values below 1e-7 of the stress scale,
+    i.e. the lateral components and the elastic-regime shear, are noise in the golden itself)."""
+    r, gold = _run(orc, "voce_pa", 40)
+    s = r["stress"]
+    off, worst = 0, 0.0
+    for i in range(40):
+        for c in range(2, 6):
+            if abs(gold[i, c]) < 1e-4:   # print resolution finer than 1e-9 GPa = 2e-8 of the axial stress
+                continue
+            d = abs(float("%.6g" % s[i, c]) - gold[i, c]) / _ulp6(gold[i, c])
+            off += d > 0.5
+            worst = max(worst, d)
+    assert worst <= 1.5, worst          # at most the last digit, by one
+    assert off <= 50, off               # about 40 of 150 at this commit
 
 
 def test_plastic_work_and_dp_goldens(orc):
@@ -47,10 +98,10 @@ def test_plastic_work_and_dp_goldens(orc):
     r, gold = _run(orc, "voce_ea", 8)
     plw = r["extra"][:8, 0]
     gp = g["voce_ea_pl_work"][:8]
-    assert np.abs(plw - gp).max() / np.abs(gp).max() < 2e-4
+    assert (np.abs(plw - gp)[1:] / np.abs(gp)[1:]).max() < 3e-5      # each row relative to itself (row 1 is zero work)
     dp = r["extra"][:8, 1:7]
     gd = g["voce_ea_dp_tensor"][:8]
-    assert np.abs(dp - gd).max() / np.abs(gd).max() < 2e-4
+    assert np.abs(dp - gd).max() / np.abs(gd).max() < 1.5e-5
     # volume-averaged deformation gradient (voce_ea_def_grad.txt, values ~1 printed with 6 digits)
     assert np.abs(r["extra"][:8, 7:16] - g["voce_ea_def_grad"][:8]).max() < 6e-6
 
@@ -60,8 +111,8 @@ def test_additional_averages_constant_strain_rate(orc):
     g = refcases.goldens()
     r, gold = _run(orc, "voce_ea_cs", 10)
     gp, gd, gF = g["voce_ea_cs_pl_work"][:10], g["voce_ea_cs_dp_tensor"][:10], g["voce_ea_cs_def_grad"][:10]
-    assert np.abs(r["extra"][:10, 0] - gp).max() / np.abs(gp).max() < 2e-4
-    assert np.abs(r["extra"][:10, 1:7] - gd).max() / np.abs(gd).max() < 2e-4
+    assert (np.abs(r["extra"][:10, 0] - gp)[1:] / np.abs(gp)[1:]).max() < 3e-5
+    assert np.abs(r["extra"][:10, 1:7] - gd).max() / np.abs(gd).max() < 1.5e-5
     assert np.abs(r["extra"][:10, 7:16] - gF).max() < 6e-6
 
 
@@ -72,13 +123,14 @@ def test_cyclic_reversal(orc):
     r = orc.sim_run(**inp)
     assert r["rc"] == 0
     err = np.abs(r["stress"][:, 2] - gold[:14, 2]).max() / np.abs(gold[:14, 2]).max()
-    assert err < 3e-5, err
+    assert err < 2.5e-5, err
+    assert np.abs(r["stress"][:, 3:] - gold[:14, 3:]).max() / np.abs(gold[:14, 2]).max() < 5e-7
 
 
 def test_constant_strain_rate_bcs(orc):
     """voce_ea_cs_stress.txt: velocity-gradient ("constant strain rate") boundary conditions, EA assembly."""
     r, gold = _run(orc, "voce_ea_cs", 40)   # the whole history
-    _check(r, gold)
+    _check(r, gold, VOCE)
 
 
 @pytest.mark.parametrize("name,nsteps", [("voce_full_cyclic_cs", 13), ("voce_full_cyclic_csm", 70)])
@@ -90,7 +142,8 @@ def test_cyclic_constant_strain_rate(orc, name, nsteps):
     r = orc.sim_run(**inp)
     assert r["rc"] == 0
     err = np.abs(r["stress"][:, 2] - gold[:nsteps, 2]).max() / np.abs(gold[:nsteps, 2]).max()
-    assert err < 3e-5, err
+    assert err < 2.5e-5, err
+    assert np.abs(r["stress"][:, 3:] - gold[:nsteps, 3:]).max() / np.abs(gold[:nsteps, 2]).max() < 5e-7
 
 
 def test_auto_time_stepping(orc):
@@ -115,4 +168,4 @@ def test_auto_time_stepping(orc):
         t += dts[k]
         dt_class = max(at["dt_min"], dts[k] * (inp["nr"][2] * at["dt_scale"]) / nit[k])
     err = np.abs(r["stress"][0] - gold[0]) / abs(gold[0, 2])
-    assert err.max() < TOL, err.max()
+    assert err.max() < 1.5e-5, err.max()
