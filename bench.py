@@ -100,9 +100,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(n, ngrains, seed):
+def workload(n, ngrains, seed, nz=None):
     from exaconstit_b200 import voxel
-    grains = voxel.voronoi_grains(n, n, n, ngrains, seed)
+    grains = voxel.voronoi_grains(n, n, nz or n, ngrains, seed)
     quats = voxel.random_quats(ngrains, seed + 1)
     return grains, quats
 
@@ -132,8 +132,9 @@ def run_ours(args):
         nccl_id = bytes(idt.cpu().tolist())
     n = args.n
     ngrains, seed = grains_for(n, args.grains)
-    grains, quats = workload(n, ngrains, seed)
-    sim = host.VoxelSim((n, n, n), (1.0, 1.0, 1.0), 0, 0, PROPS_VOCE, 298.0, grains, quats, assembly=0,
+    nz = args.nz or n
+    grains, quats = workload(n, ngrains, seed, nz)
+    sim = host.VoxelSim((n, n, nz), (1.0, 1.0, nz / n), 0, 0, PROPS_VOCE, 298.0, grains, quats, assembly=0,
                         nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, args.krylov_iter), true_jacobi=args.true_jacobi,
                         rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
     if nranks > 1 and not args.nccl_only:
@@ -196,7 +197,7 @@ def run_ours(args):
             "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_FMT % (n, ngrains, args.krylov_iter),
-                       "mesh": [n, n, n], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi),
+                       "mesh": [n, n, nz], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi),
                        "cache": "inputs >> L2 (%.1f GB of quadrature data per rank)" % (ne_local * 8 * (36 + 9 + 2 * 28 + 12) * 8 / 1e9),
                        "newton_iters": newton, "pcg_iters": pcg, "model_setups": setups, "grad_mults": gmults},
             "e2e": {"value": newton / (e2e_ms * 1e-3), "unit": "Newton-steps/s",
@@ -220,6 +221,11 @@ def run_ours(args):
             "avg_stress_zz_last": float(timed[-1]["avg_stress"][2]),
             "all_steps_converged": bool(all(s["converged"] for s in timed)),
             "wall_ms": wall_ms,
+            # where the step goes (rank 0's kernels, CUDA events): the PCG operator apply, the material update, and the rest
+            # (CG vector kernels, exchanges, residual / Jacobians / averages, host waits)
+            "step_anatomy": {"k2_grad_mult": gm_ms / dev_ms, "k1_model_setup": ms_ms / dev_ms,
+                             "other": 1.0 - (gm_ms + ms_ms) / dev_ms, "us_per_pcg_iteration": dev_ms * 1e3 / max(pcg, 1),
+                             "us_per_pcg_iteration_outside_k1": (dev_ms - ms_ms) * 1e3 / max(pcg, 1)},
         }
         if nranks == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(n, args.krylov_iter, args.warmup, budget_s=args.cpu_budget)
@@ -259,6 +265,8 @@ FINGERPRINT = os.path.join(ROOT, "tests", "golden", "bench_fingerprint.json")
 
 
 def check_fingerprint(n, ngrains, args, steps):
+    if args.nz and args.nz != n:
+        return {"checked": False, "why": "slab diagnostic run"}
     """Parity evidence inside the bench: the volume-averaged stress history of this run (any number of ranks) against
     the stored 1-GPU history of the same workload (tools/make_bench_fingerprint.py), relative to the step's largest
     component.  The 1-GPU history itself is tied to the oracle by tests/test_gpu_system.py at 8^3 and 32^3."""
@@ -421,6 +429,8 @@ def parse_args(argv=None):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="voxels per edge (default: the 128^3 headline workload)")
+    ap.add_argument("--nz", type=int, default=0, help="element layers in z (default n); a slab of the workload, e.g. one "
+                    "rank's share of an 8-GPU run on one GPU (diagnostics, not a bench line)")
     ap.add_argument("--grains", type=int, default=0, help="grain count (default: BASELINE.json's for the mesh size)")
     ap.add_argument("--krylov-iter", type=int, default=1000)
     ap.add_argument("--true-jacobi", action="store_true")

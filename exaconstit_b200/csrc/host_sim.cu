@@ -511,6 +511,89 @@ __global__ void __launch_bounds__(256) k_cg_step1_fused(double* __restrict__ x, 
   }
 }
 
+// The whole vector part of a CG iteration in ONE launch: step 1 (x += alpha d, r -= alpha z, betanom = r.Mr with the
+// block reduction, the fixed-order final sum and -- for nranks > 1 -- the peer-memory all-reduce done by the last
+// block to arrive), a grid-wide barrier on a generation flag, then step 2 (d = M r + beta d, z = 0) on the same
+// slices while r is still in L2.  Replaces k_cg_step1_fused + k_cg_step2 (one launch and one full re-read of r and d
+// less per iteration).  All blocks must be co-resident (the grid is sized from the occupancy query by the caller).
+__global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double* __restrict__ r, double* __restrict__ d,
+                                                  double* __restrict__ z, const double* __restrict__ dinv,
+                                                  const double* __restrict__ nom, const double* __restrict__ den, long nn,
+                                                  long n_owned, double* __restrict__ partial, double* __restrict__ den_next,
+                                                  unsigned int* __restrict__ counter, double* __restrict__ d_bet,
+                                                  PeerTable peers, int rank, int nranks, unsigned long long seq,
+                                                  unsigned long long* __restrict__ gen_flag, unsigned long long gen) {
+  const double nom_v = *nom;
+  const double alpha = nom_v / *den;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
+  double s = 0.0;
+  for (int c = 0; c < 3; ++c) {
+    const long off = c * nn;
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
+      const long i = off + n;
+      x[i] += alpha * d[i];
+      const double rn = r[i] - alpha * z[i];
+      r[i] = rn;
+      z[i] = 0.0;  // output of the next operator apply
+      if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+    }
+  }
+  __shared__ double red[8];
+  __shared__ bool last;
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;  // wraps back to 0 for the next launch
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double t = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) t += ld_cg(&partial[i]);
+    for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) {
+        double u = 0.0;
+        for (int w = 0; w < 8; ++w) u += red[w];
+        *d_bet = u;
+      }
+      __syncwarp();
+      if (nranks > 1) warp_allreduce_p2p(d_bet, peers, rank, nranks, 1, seq, threadIdx.x);
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(gen_flag), "l"(gen) : "memory");
+      }
+    }
+  }
+  // grid barrier: everyone waits for this launch's generation
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(gen_flag) : "memory");
+      if (v < gen) __nanosleep(40);
+    } while (v < gen);
+  }
+  __syncthreads();
+  const double beta = ld_cg(d_bet) / nom_v;
+  for (int c = 0; c < 3; ++c) {
+    const long off = c * nn;
+    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
+      const long i = off + n;
+      const double ri = r[i];
+      d[i] = (dinv ? dinv[i] * ri : ri) + beta * d[i];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- communicator --------------
 class SlabComm {
  public:
@@ -632,6 +715,30 @@ class SlabComm {
     k_cg_step1_fused<<<kRedBlocks, 256, 0, stream>>>(x, r, d, z, dinv, d_nom, d_den, nn, n_owned, partial.d, d_den_next,
                                                      reinterpret_cast<unsigned int*>(counter.d), d_bet, peers, rank,
                                                      nranks, seq_scal);
+  }
+  // whole vector part of a CG iteration in one launch (k_cg_fused); false if this configuration has to use the
+  // separate kernels (NCCL-only exchanges, or a grid that could not be made co-resident)
+  int fused_grid = -1;
+  unsigned long long fused_gen = 0;
+  bool CgFused(double* x, double* r, double* d, double* z, const double* dinv, const double* d_nom, const double* d_den,
+               double* d_den_next, double* d_bet) {
+    if (nranks > 1 && !use_p2p) return false;
+    if (fused_grid < 0) {
+      int dev = 0, sms = 0, occ = 0;
+      HCK(cudaGetDevice(&dev));
+      HCK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      HCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_fused, 256, 0));
+      fused_grid = std::min<long>(kRedBlocks, (long)sms * occ);
+      if (std::getenv("EXAHOST_NO_CG_FUSION")) fused_grid = 0;
+    }
+    if (fused_grid <= 0) return false;
+    ++g_host_launches;
+    if (nranks > 1) { ++seq_scal; ++n_allreduce; }
+    ++fused_gen;
+    k_cg_fused<<<fused_grid, 256, 0, stream>>>(x, r, d, z, dinv, d_nom, d_den, nn, n_owned, partial.d, d_den_next,
+                                               reinterpret_cast<unsigned int*>(counter.d), d_bet, peers, rank, nranks, seq_scal,
+                                               reinterpret_cast<unsigned long long*>(counter.d) + 1, fused_gen);
+    return true;
   }
   // partial sums -> one device scalar (+ allreduce), no host involvement
   void ReduceToDevice(double* d_out) {
@@ -917,14 +1024,16 @@ class CGSolver {
       const int a = (i - 1) & 1;
       double* d_nom = scal.d + a; double* d_bet = scal.d + (a ^ 1);
       double* d_den = scal.d + 2 + a; double* d_den_next = scal.d + 2 + (a ^ 1);
-      comm->CgStep1(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, d_den_next, d_bet);
+      // step 1 and (speculatively: it touches neither x nor r) the next direction d = M r + beta d with z zeroed
+      const bool fused = comm->CgFused(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, d_den_next, d_bet);
+      if (!fused) comm->CgStep1(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, d_den_next, d_bet);
       const int slot = i & 7;
       HCK(cudaMemcpyAsync(h_bet + slot, d_bet, sizeof(double), cudaMemcpyDeviceToHost, stream));
       HCK(cudaEventRecord(ev[slot], stream));
       const bool last = (i + 1 > max_iter);
       if (!last) {
-        // speculative: next direction and operator apply (do not touch x, r)
-        k_cg_step2<<<nb(n), 256, 0, stream>>>(d.d, r.d, dinv, z.d, d_bet, d_nom, n);
+        // speculative operator apply
+        if (!fused) k_cg_step2<<<nb(n), 256, 0, stream>>>(d.d, r.d, dinv, z.d, d_bet, d_nom, n);
         A->MultAccDot(d, z, d_den_next);
       }
       HCK(cudaEventSynchronize(ev[slot]));

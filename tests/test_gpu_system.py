@@ -46,9 +46,10 @@ def test_time_history_matches_oracle_and_golden(orc, name, nsteps):
         sc = max(np.abs(hr[:, c]).max(), 1e-12)
         assert np.abs(hg[:, c] - hr[:, c]).max() / sc < 1e-7, c
     assert np.abs(state["stress"] - ref["stress_qp"]).max() / np.abs(ref["stress_qp"]).max() < 1e-8
-    # against the reference's golden file: 6 printed digits
+    # against the reference's golden file (6 printed digits): the Voce family to the print resolution, KMBalD to 1.6e-5
+    # (tests/test_oracle_goldens.py has the per-case record)
     err = np.abs(s_gpu - gold) / np.abs(gold[:, 2:3])
-    assert err.max() < 1.5e-5
+    assert err.max() < (1.6e-5 if name.startswith("mtsdd") else 4e-6)
     assert launches > 0
 
 
@@ -192,6 +193,52 @@ def test_config5_small_hcp_bbar_ea_nrls_cyclic(orc):
     s = np.array([h["avg_stress"] for h in hist])
     assert (np.abs(s - ref["stress"]) / np.abs(ref["stress"]).max()).max() < 1e-8
     assert [h["newton_iters"] for h in hist] == list(ref["iters"][:, 0])
+
+
+def _config_parity(orc, n, grains, quats, dts, tol=1e-8):
+    """GPU host layer vs the oracle's simulation on a BASELINE.json configuration: averaged stress to `tol` of the
+    loaded component, identical Newton counts, PCG counts within 2, end state to 1e-7."""
+    from exaconstit_b200 import host
+    import bench
+    common = dict(props=bench.PROPS_VOCE, temp_k=298.0, grain_ids=grains, quats=quats, assembly=0, nr=(5e-5, 5e-10, 25),
+                  kr=(1e-7, 1e-27, 1000))
+    sim = host.VoxelSim((n, n, n), (1.0, 1.0, 1.0), 0, 0, **common)
+    hist = sim.run(dts, [(1,) + bench.BC])
+    state = dict(stress=sim.get("stress"), hist=sim.get("hist"))
+    sim.close()
+    ref = orc.sim_run((n, n, n), (1.0, 1.0, 1.0), 0, 0, dts=dts, bcs=[(1,) + bench.BC], want_state=True, **common)
+    assert ref["rc"] == 0 and ref["stats"]["failed_points"] == 0 and all(h["converged"] for h in hist)
+    s = np.array([h["avg_stress"] for h in hist])
+    assert (np.abs(s - ref["stress"]) / np.abs(ref["stress"][:, 2:3])).max() < tol
+    assert [h["newton_iters"] for h in hist] == list(ref["iters"][:, 0])
+    assert np.abs(np.array([h["pcg_iters"] for h in hist]) - ref["iters"][:, 1]).max() <= 2
+    assert np.abs(state["stress"] - ref["stress_qp"]).max() / np.abs(ref["stress_qp"]).max() < tol
+    hg, hr = state["hist"].reshape(-1, 28), ref["hist"].reshape(-1, 28)
+    for c in range(28):
+        if c != 3:
+            assert np.abs(hg[:, c] - hr[:, c]).max() / max(np.abs(hr[:, c]).max(), 1e-12) < 1e-7, c
+    return s
+
+
+def test_baseline_config_1_whole_history_matches_oracle(orc):
+    """BASELINE.json configs[0]: 8^3 voxels, 4 grains in 2x2x1 blocks of 4x4x8 voxels (deterministic, no
+    RNG), FCC Voce, PA, the reference's 40-step dt schedule."""
+    import bench
+    k, j, i = np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij")
+    grains = (1 + (i // 4) + 2 * (j // 4)).ravel().astype(np.int32)
+    quats = refcases.goldens()["voce_quats"][:4]
+    s = _config_parity(orc, 8, grains, quats, bench.dt_schedule(40))
+    assert s[-1, 2] > s[0, 2] > 0
+
+
+def test_baseline_config_2_matches_oracle(orc):
+    """BASELINE.json configs[1] at its full size: 32^3 voxels, 100 Voronoi grains (seed 32100), FCC Voce, PA + PCG; the
+    first three steps of the schedule (elastic, yield, plastic) against the oracle run on the host cores."""
+    import bench
+    ngrains, seed = bench.grains_for(32)
+    grains, quats = bench.workload(32, ngrains, seed)
+    orc.use_all_host_threads()
+    _config_parity(orc, 32, grains, quats, bench.dt_schedule(3))
 
 
 @pytest.mark.parametrize("n,xtal,kin,props_key,ngrains", [(32, 0, 0, "props_cp_voce", 100), (64, 1, 2, "props_cp_mts", 500)])
