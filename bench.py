@@ -142,7 +142,10 @@ def run_ours(args):
     for tv in args.tuning:
         c, v = tv.split(":")
         sim.set_tuning(int(c), int(v))
-    mask, ess_val = sim.set_bcs(*BC)
+    bc = BC
+    if nz != n:  # slab diagnostic: same axial strain rate as the cube
+        bc = (BC[0], BC[1], [[v * nz / n for v in row] for row in BC[2]])
+    mask, ess_val = sim.set_bcs(*bc)
     ess_pinned = np.ascontiguousarray(ess_val)
     vel_out = np.zeros(3 * sim.nnodes)
 

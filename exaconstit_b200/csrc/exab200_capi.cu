@@ -56,6 +56,10 @@ struct exab200_ctx {
   CUtensorMap tmap;
   bool tmap_valid = false;
   int variant_c = 30, ctas_c = 6;
+  // operator apply with the interface-plane exchange folded in (exab200_grad_mult_halo)
+  unsigned long long* d_halo_cnt = nullptr;
+  unsigned long long halo_tiles_cum = 0, halo_ctas_cum = 0;
+  int halo_ctas = 8;
   int variant_ea = 40, ctas_ea = 3;
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
@@ -163,7 +167,31 @@ static int launch_gmc(exab200_ctx* c, const double* x, double* y, ElemIO io, cud
   long grid = (long)c->sm_count * c->ctas_c;
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
   k_grad_mult_pa_c<NW, STAGES, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->tmap, x, y, io, c->cfg.nelems, c->grad_dt, dot,
-                                                                           c->d_xend);
+                                                                           c->d_xend, HaloArgs{});
+  POST_LAUNCH(c);
+  return 0;
+}
+// the same kernel with the interface-plane exchange and the all-reduce of the denominator folded in
+template <bool ESS>
+static int launch_gmc_halo(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot, HaloArgs h) {
+  constexpr int NW = 2, STAGES = 2;
+  constexpr int smem = NW * STAGES * kWarpStageBytesC + NW * STAGES * 8 + 1024;
+  static bool attr_set_dev[64] = {};
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_grad_mult_pa_c<NW, STAGES, ESS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long nwt = (c->cfg.nelems + 3) / 4;
+  long compute = (long)c->sm_count * c->ctas_c - h.ncomm;   // the exchange CTAs take the place of compute CTAs: one wave
+  if (compute * NW > nwt) compute = (nwt + NW - 1) / NW;
+  c->halo_tiles_cum += (unsigned long long)(h.nb_lo + h.nb_hi);
+  c->halo_ctas_cum += (unsigned long long)compute;
+  h.counters = c->d_halo_cnt;
+  h.tiles_target = c->halo_tiles_cum;
+  h.ctas_target = c->halo_ctas_cum;
+  k_grad_mult_pa_c<NW, STAGES, ESS, true><<<(unsigned)(compute + h.ncomm), NW * 32, smem, st>>>(c->tmap, x, y, io, c->cfg.nelems,
+                                                                                               c->grad_dt, dot, c->d_xend, h);
   POST_LAUNCH(c);
   return 0;
 }
@@ -362,6 +390,7 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_e2n);
   cudaFree(c->d_ess);
   cudaFree(c->d_fail);
+  cudaFree(c->d_halo_cnt);
   cudaFree(c->d_ea);
   cudaFree(c->d_xend);
   cudaFree(c->d_tan);
@@ -546,6 +575,48 @@ int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int
   }
   if (ess) return launch_grad_mult_pa<LVEC, true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
   return launch_grad_mult_pa<LVEC, false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+}
+
+int exab200_grad_mult_halo_supported(exab200_ctx* c, const exab200_halo* h) {
+  if (!c || !h || !c->cfg.nnodes) return 0;
+  if (c->cfg.assembly != EXAB200_PA || !c->tangent_fmt) return 0;          // compact-record PA kernel only
+  if (h->nranks < 2 || h->nranks > 8 || h->layer_elems <= 0 || c->cfg.nelems % h->layer_elems) return 0;
+  const long layers = c->cfg.nelems / h->layer_elems;
+  const long nwt = (c->cfg.nelems + 3) / 4, nb_lo = (h->layer_elems + 3) / 4, hi_start = (c->cfg.nelems - h->layer_elems) / 4;
+  if (layers < 3 || hi_start < nb_lo || nwt < 64) return 0;                // the two boundary layers must be distinct tiles
+  return 1;
+}
+
+int exab200_grad_mult_halo(exab200_ctx* c, const double* d_x_L, double* d_y_L, int flags, double* d_dot_accum,
+                           const exab200_halo* hd, void* stream) {
+  NEED_L(c);
+  if (!c->d_matgrad) return fail("grad_setup has not been called");
+  if (!exab200_grad_mult_halo_supported(c, hd)) return fail("exab200_grad_mult_halo: unsupported configuration (see exab200_grad_mult_halo_supported)");
+  if (!(c->d_xend && c->xend_jac == c->d_jac))
+    return fail("compact tangent records need the Jacobian array written by the last exab200_setup_jacobians call");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!c->d_halo_cnt) {
+    CK(cudaMalloc(&c->d_halo_cnt, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(c->d_halo_cnt, 0, 2 * sizeof(unsigned long long)));
+    if (const char* e = std::getenv("EXAB200_HALO_CTAS")) c->halo_ctas = std::max(1, std::min(64, std::atoi(e)));
+  }
+  const bool local_action = flags & EXAB200_LOCAL_ACTION;
+  if (!(flags & EXAB200_NO_ZERO)) CK(cudaMemsetAsync(d_y_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
+  const bool ess = c->have_ess && !local_action;
+  ElemIO io{c->d_e2n, ess ? c->d_ess : nullptr, c->cfg.nnodes};
+  HaloArgs h{};
+  h.mb = hd->mailbox; h.lo = hd->lo; h.hi = hd->hi;
+  for (int r = 0; r < 8; ++r) h.peers.p[r] = hd->peers[r];
+  h.peers.spin_limit = hd->spin_limit;
+  h.rank = hd->rank; h.nranks = hd->nranks; h.ncomm = c->halo_ctas;
+  h.nn = c->cfg.nnodes; h.plane = hd->plane;
+  const long nwt = (c->cfg.nelems + 3) / 4;
+  h.nb_lo = hd->lo ? (hd->layer_elems + 3) / 4 : 0;
+  h.hi_start = (c->cfg.nelems - hd->layer_elems) / 4;
+  h.nb_hi = hd->hi ? nwt - h.hi_start : 0;
+  h.seq_halo = hd->seq_halo; h.seq_scal = hd->seq_scal;
+  if (ess) return launch_gmc_halo<true>(c, d_x_L, d_y_L, io, st, d_dot_accum, h);
+  return launch_gmc_halo<false>(c, d_x_L, d_y_L, io, st, d_dot_accum, h);
 }
 
 int exab200_grad_mult(exab200_ctx* c, const double* d_x_L, double* d_y_L, int local_action, void* stream) {

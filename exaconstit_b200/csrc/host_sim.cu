@@ -31,6 +31,7 @@
 
 #include "../../include/exab200.h"
 #include "../../include/exahost.h"
+#include "exab200_p2p.cuh"
 
 namespace exahost {
 
@@ -323,68 +324,12 @@ struct KernelTimer {
 };
 
 // ---------------------------------------------------------------- NVLink peer-memory collectives
-// Every rank owns a small "mailbox" in device memory that its peers map through CUDA IPC.  The two
-// latency-critical exchanges of the CG loop are done by single kernels that store straight into the
-// peers' mailboxes over NVLink and synchronise through release/acquire flags there:
-//   * interface-plane sum with the z-neighbours (k_halo_p2p)
-//   * all-reduce of up to 8 scalars over all ranks, summed in rank order => bitwise identical on every
-//     rank and run to run (k_allreduce_p2p)
-// Sequence numbers are monotonic and slots are double-buffered by parity, which is sufficient because a
-// rank can only be one collective ahead of a peer it exchanges with.
-// Mailbox layout (doubles): [0,64) flags as u64: 0 halo-from-lo, 1 halo-from-hi, 8+r scalar-from-rank-r,
-// 16 block counter, 17 error;  [64,192) scalar slots [par][rank][8];  [192, 192+12*plane) halo slots
-// [from-lo | from-hi][par][3*plane].
-constexpr int kMbScal = 64, kMbHalo = 192;
-// A lost peer becomes an error instead of a hang: after the limit (clock64 ticks, ~10 s by default;
-// EXAHOST_SPIN_LIMIT_S overrides) the waiter raises the mailbox error flag AND poisons what it was about to
-// produce with NaN, so that the CG scalars turn non-finite and the host loop stops at its next stopping test
-// instead of iterating on stale data (the flag is then reported as the cause).
-__device__ long long g_spin_limit = 20000000000LL;
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq, double* mb) {
-  const long long t0 = clock64();
-  while (ld_acquire_sys(flag) < seq) {
-    if (clock64() - t0 > g_spin_limit) { reinterpret_cast<unsigned long long*>(mb)[17] = 1ull; return false; }
-  }
-  return true;
-}
-__device__ __forceinline__ double ld_cg(const double* p) {
-  double v;
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-
-// v: local L-vector; mb: my mailbox; lo/hi: peers' mailboxes (nullptr at the ends of the rank line)
-struct PeerTable { double* p[8]; };
-
-// one warp: in-place sum of val[0..n) over all ranks through the peers' scalar slots (rank order)
-__device__ __forceinline__ void warp_allreduce_p2p(double* val, const PeerTable& peers, int rank, int nranks, int n,
-                                                   unsigned long long seq, int lane) {
-  const int par = (int)(seq & 1);
-  double* mb = peers.p[rank];
-  if (lane < nranks) {
-    double* dst = peers.p[lane] + kMbScal + (par * 8 + rank) * 8;
-    for (int k = 0; k < n; ++k) dst[k] = val[k];
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long*>(peers.p[lane]) + 8 + rank, seq);
-  }
-  const bool ok = (lane < nranks) ? spin_until(reinterpret_cast<unsigned long long*>(mb) + 8 + lane, seq, mb) : true;
-  const bool all_ok = __all_sync(0xffffffffu, ok);
-  __syncwarp();
-  if (lane < n) {
-    double s = 0.0;
-    for (int r = 0; r < nranks; ++r) s += ld_cg(&mb[kMbScal + (par * 8 + r) * 8 + lane]);
-    val[lane] = all_ok ? s : __longlong_as_double(0x7ff8000000000000LL);
-  }
-}
+// protocol and device helpers: exab200_p2p.cuh
+using exab_p2p::PeerTable;
+using exab_p2p::warp_allreduce_p2p;
+using exab_p2p::ld_cg;
+using exab_p2p::kMbScal;
+using exab_p2p::kMbHalo;
 
 // The last block (when ar_val != nullptr) is not part of the plane exchange: it all-reduces one scalar
 // (the CG denominator accumulated by the operator kernel) in the same launch.
@@ -396,38 +341,8 @@ __global__ void __launch_bounds__(256) k_halo_p2p(double* __restrict__ v, double
     if (threadIdx.x < 32) warp_allreduce_p2p(ar_val, peers, rank, nranks, 1, seq_scal, threadIdx.x);
     return;
   }
-  const int par = (int)(seq & 1);
-  const long n3 = 3 * plane, top = nn - plane;
   __shared__ bool s_ok;
-  // push: my bottom plane -> lower neighbour's "from-hi" slot, my top plane -> upper neighbour's "from-lo" slot
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)nblk * blockDim.x) {
-    const long c = i / plane, n = i - c * plane;
-    if (lo) lo[kMbHalo + (2 + par) * n3 + i] = v[c * nn + n];
-    if (hi) hi[kMbHalo + (0 + par) * n3 + i] = v[c * nn + top + n];
-  }
-  __threadfence_system();
-  __syncthreads();
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(mb);
-  if (threadIdx.x == 0) {
-    const unsigned long long prev = atomicAdd(&flags[16], 1ull);
-    if (prev == nblk - 1) {
-      flags[16] = 0ull;
-      __threadfence_system();
-      if (lo) st_release_sys(reinterpret_cast<unsigned long long*>(lo) + 1, seq);  // I am the lower one's "hi"
-      if (hi) st_release_sys(reinterpret_cast<unsigned long long*>(hi) + 0, seq);  // I am the upper one's "lo"
-    }
-    bool ok = true;
-    if (lo) ok = spin_until(&flags[0], seq, mb) && ok;
-    if (hi) ok = spin_until(&flags[1], seq, mb) && ok;
-    s_ok = ok;
-  }
-  __syncthreads();
-  const double poison = s_ok ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long)nblk * blockDim.x) {
-    const long c = i / plane, n = i - c * plane;
-    if (lo) v[c * nn + n] += ld_cg(&mb[kMbHalo + (0 + par) * n3 + i]) + poison;
-    if (hi) v[c * nn + top + n] += ld_cg(&mb[kMbHalo + (2 + par) * n3 + i]) + poison;
-  }
+  exab_p2p::halo_exchange_blocks(v, mb, lo, hi, nn, plane, seq, peers.spin_limit, blockIdx.x, nblk, &s_ok);
 }
 
 // in-place sum of val[0..n) over all ranks, n <= 8; one warp
@@ -522,7 +437,8 @@ __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double
                                                   long n_owned, double* __restrict__ partial, double* __restrict__ den_next,
                                                   unsigned int* __restrict__ counter, double* __restrict__ d_bet,
                                                   PeerTable peers, int rank, int nranks, unsigned long long seq,
-                                                  unsigned long long* __restrict__ gen_flag, unsigned long long gen) {
+                                                  unsigned long long* __restrict__ gen_flag, unsigned long long gen,
+                                                  volatile double* __restrict__ host_bet /* mapped pinned: {betanom, gen} */) {
   const double nom_v = *nom;
   const double alpha = nom_v / *den;
   if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
@@ -571,6 +487,11 @@ __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double
       if (threadIdx.x == 0) {
         __threadfence();
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(gen_flag), "l"(gen) : "memory");
+        // the host's stopping test reads betanom straight from mapped pinned memory (no copy-engine op and no event
+        // between this kernel and the operator apply that follows it in the stream)
+        host_bet[0] = *d_bet;
+        __threadfence_system();
+        host_bet[1] = __longlong_as_double((long long)gen);
       }
     }
   }
@@ -615,9 +536,10 @@ class SlabComm {
     if (nranks_ < 1 || nranks_ > 8 || rank_ < 0 || rank_ >= nranks_)
       throw Abort{"SlabComm: 1 <= nranks <= 8 (one box of NVLink peers: PeerTable and the mailbox layout hold 8 ranks) and 0 <= rank < nranks"};
     rank = rank_; nranks = nranks_; stream = s; nn = nn_; plane = plane_;
+    peers.spin_limit = 20000000000LL;  // ~10 s of clock64 ticks; EXAHOST_SPIN_LIMIT_S overrides
     if (const char* e = std::getenv("EXAHOST_SPIN_LIMIT_S")) {
       const long long ticks = (long long)(std::atof(e) * 2.0e9);
-      if (ticks > 0) HCK(cudaMemcpyToSymbol(g_spin_limit, &ticks, sizeof(ticks)));
+      if (ticks > 0) peers.spin_limit = ticks;
     }
     n_owned = (rank == nranks - 1) ? nn : nn - plane;
     partial.SetSize(kRedBlocks);
@@ -663,6 +585,36 @@ class SlabComm {
     for (void* p : opened) cudaIpcCloseMemHandle(p);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     if (h_scal) cudaFreeHost(h_scal);
+    if (h_poll) cudaFreeHost(const_cast<double*>(h_poll));
+  }
+  // operator apply with the exchange folded in (exab200_grad_mult_halo): decided once per context
+  int halo_fused = -1;
+  bool HaloFusedOk(exab200_ctx* ctx, long layer_elems) {
+    if (halo_fused < 0) {
+      halo_fused = 0;
+      if (use_p2p && nranks > 1 && !std::getenv("EXAHOST_NO_HALO_FUSION")) {
+        exab200_halo h = MakeHaloDescriptor(layer_elems);
+        halo_fused = exab200_grad_mult_halo_supported(ctx, &h);
+      }
+    }
+    return halo_fused == 1;
+  }
+  exab200_halo MakeHaloDescriptor(long layer_elems) const {
+    exab200_halo h;
+    std::memset(&h, 0, sizeof(h));
+    h.mailbox = mailbox.d;
+    h.lo = rank > 0 ? peers.p[rank - 1] : nullptr;
+    h.hi = rank < nranks - 1 ? peers.p[rank + 1] : nullptr;
+    for (int r = 0; r < nranks; ++r) h.peers[r] = peers.p[r];
+    h.spin_limit = peers.spin_limit;
+    h.rank = rank; h.nranks = nranks;
+    h.plane = plane; h.layer_elems = layer_elems;
+    h.seq_halo = seq_halo; h.seq_scal = seq_scal;
+    return h;
+  }
+  exab200_halo NextHaloDescriptor(long layer_elems) {
+    ++seq_halo; ++seq_scal; ++n_halo; ++n_allreduce;
+    return MakeHaloDescriptor(layer_elems);
   }
   // Sum the partial results living on the interface planes with the z-neighbours (the role of
   // P->MultTranspose followed by P->Mult in the reference, src/mechanics_operator_ext.cpp:149,157).
@@ -720,6 +672,8 @@ class SlabComm {
   // separate kernels (NCCL-only exchanges, or a grid that could not be made co-resident)
   int fused_grid = -1;
   unsigned long long fused_gen = 0;
+  volatile double* h_poll = nullptr;  // mapped pinned {betanom, generation}
+  double* d_poll = nullptr;
   bool CgFused(double* x, double* r, double* d, double* z, const double* dinv, const double* d_nom, const double* d_den,
                double* d_den_next, double* d_bet) {
     if (nranks > 1 && !use_p2p) return false;
@@ -730,6 +684,13 @@ class SlabComm {
       HCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cg_fused, 256, 0));
       fused_grid = std::min<long>(kRedBlocks, (long)sms * occ);
       if (std::getenv("EXAHOST_NO_CG_FUSION")) fused_grid = 0;
+      if (fused_grid > 0) {
+        void* hp = nullptr;
+        HCK(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+        std::memset(hp, 0, 64);
+        h_poll = static_cast<volatile double*>(hp);
+        HCK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_poll), hp, 0));
+      }
     }
     if (fused_grid <= 0) return false;
     ++g_host_launches;
@@ -737,8 +698,28 @@ class SlabComm {
     ++fused_gen;
     k_cg_fused<<<fused_grid, 256, 0, stream>>>(x, r, d, z, dinv, d_nom, d_den, nn, n_owned, partial.d, d_den_next,
                                                reinterpret_cast<unsigned int*>(counter.d), d_bet, peers, rank, nranks, seq_scal,
-                                               reinterpret_cast<unsigned long long*>(counter.d) + 1, fused_gen);
+                                               reinterpret_cast<unsigned long long*>(counter.d) + 1, fused_gen, d_poll);
     return true;
+  }
+  // betanom of the last CgFused launch; spins on the mapped word (checks the stream now and then so that a failed
+  // launch cannot hang the host)
+  double WaitBetanom() {
+    unsigned long spins = 0;
+    for (;;) {
+      const double tag = h_poll[1];
+      long long t;
+      std::memcpy(&t, &tag, 8);
+      if ((unsigned long long)t == fused_gen) return h_poll[0];
+      if ((++spins & 0xfffff) == 0) {
+        const cudaError_t q = cudaStreamQuery(stream);
+        if (q != cudaErrorNotReady) {
+          const double tag2 = h_poll[1];
+          std::memcpy(&t, &tag2, 8);
+          if ((unsigned long long)t == fused_gen) return h_poll[0];
+          throw Abort{std::string("CG: the vector kernel did not deliver its result: ") + cudaGetErrorString(q)};
+        }
+      }
+    }
   }
   // partial sums -> one device scalar (+ allreduce), no host involvement
   void ReduceToDevice(double* d_out) {
@@ -854,6 +835,7 @@ class NonlinearMechOperator : public Operator {
   mutable GradientOperator jacobian;
   Vector ess_mask_dev;           // device copy of the per-node essential mask (bytes)
   mutable long grad_mults = 0, residuals = 0;
+  long layer_elems = 0;          // elements per z-layer of the slab (exchange folded into the operator apply)
   bool need_diag = false;        // set when the smoother refreshes its inverse diagonal (true_jacobi)
   mutable KernelTimer tm_grad_mult, tm_model_setup;
 
@@ -920,10 +902,21 @@ void GradientOperator::Mult(const Vector& x, Vector& y) const {
   ++op->grad_mults;
 }
 void GradientOperator::MultAccDot(const Vector& x, Vector& y, double* d_den) const {
+  SlabComm* cm = op->comm;
+  if (cm->HaloFusedOk(op->ctx, op->layer_elems)) {
+    // one kernel: operator apply + interface-plane exchange + all-reduce of the denominator (boundary layers first,
+    // the exchange overlaps the interior)
+    exab200_halo h = cm->NextHaloDescriptor(op->layer_elems);
+    op->tm_grad_mult.Begin(op->stream);
+    XCK(exab200_grad_mult_halo(op->ctx, x.Read(), y.Write(), EXAB200_NO_ZERO, d_den, &h, op->stream));
+    op->tm_grad_mult.End(op->stream);
+    ++op->grad_mults;
+    return;
+  }
   op->tm_grad_mult.Begin(op->stream);
   XCK(exab200_grad_mult_ex(op->ctx, x.Read(), y.Write(), EXAB200_NO_ZERO, d_den, op->stream));
   op->tm_grad_mult.End(op->stream);
-  op->comm->HaloSum(y.Write(), d_den);  // interface-plane sum + all-reduce of the denominator in one launch
+  cm->HaloSum(y.Write(), d_den);  // interface-plane sum + all-reduce of the denominator in one launch
   ++op->grad_mults;
 }
 void GradientOperator::LocalMult(const Vector& x, Vector& y) const {
@@ -1028,16 +1021,19 @@ class CGSolver {
       const bool fused = comm->CgFused(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, d_den_next, d_bet);
       if (!fused) comm->CgStep1(x.d, r.d, d.d, z.d, dinv, d_nom, d_den, d_den_next, d_bet);
       const int slot = i & 7;
-      HCK(cudaMemcpyAsync(h_bet + slot, d_bet, sizeof(double), cudaMemcpyDeviceToHost, stream));
-      HCK(cudaEventRecord(ev[slot], stream));
+      if (!fused) {
+        HCK(cudaMemcpyAsync(h_bet + slot, d_bet, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        HCK(cudaEventRecord(ev[slot], stream));
+      }
       const bool last = (i + 1 > max_iter);
       if (!last) {
         // speculative operator apply
         if (!fused) k_cg_step2<<<nb(n), 256, 0, stream>>>(d.d, r.d, dinv, z.d, d_bet, d_nom, n);
         A->MultAccDot(d, z, d_den_next);
       }
-      HCK(cudaEventSynchronize(ev[slot]));
-      const double betanom = h_bet[slot];
+      double betanom;
+      if (fused) betanom = comm->WaitBetanom();
+      else { HCK(cudaEventSynchronize(ev[slot])); betanom = h_bet[slot]; }
       // mfem::CGSolver leaves the loop on betanom < 0 and on a non-positive denominator; a NaN (den == 0, or a
       // peer-memory exchange that timed out and poisoned its result) must not run max_iter applies on garbage
       if (!std::isfinite(betanom) || betanom < 0.0) { converged = 0; final_iter = i; break; }
@@ -1305,6 +1301,7 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
     s->newton->prec = s->cg.get();
     s->newton->smoother = s->smoother.get();
     s->oper->need_diag = s->smoother->refresh;
+    s->oper->layer_elems = nx * ny;
     s->newton->print_level = cfg->verbose ? 0 : -1;
     HCK(cudaMallocHost(&s->h_pinned, sizeof(double) * n));
     for (int i = 0; i < 4; ++i) HCK(cudaEventCreate(&s->ev[i]));

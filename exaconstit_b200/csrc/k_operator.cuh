@@ -5,6 +5,7 @@
 #include <cuda.h>
 
 #include "exab200_common.cuh"
+#include "exab200_p2p.cuh"
 #include "material_point.hpp"
 
 namespace exab {
@@ -393,14 +394,51 @@ __global__ void __launch_bounds__(NW * 32) k_grad_mult_pa_w(const double* __rest
 constexpr int kBoxBytes = 32 * 128;               // 32 points x 16 doubles
 constexpr int kWarpStageBytesC = 2 * kBoxBytes;   // 8192
 
+// HALO variant: the operator apply of one z-slab of a multi-GPU run WITH its interface-plane exchange and the all-reduce
+// of the fused CG denominator, in one kernel over NVLink peer memory (the role ParNonlinearForm's P^T ... P plays around
+// PANonlinearMechOperatorGradExt::TMult, src/mechanics_operator_ext.cpp:149,157).  The warp tiles of the two boundary
+// element layers are processed FIRST and counted off; the first `ncomm` CTAs do no element work: they wait for that
+// count, push this rank's partial sums on the interface planes into the neighbours' mailboxes, wait for theirs and add
+// them -- while the other CTAs stream the interior layers -- and CTA 0 finally all-reduces x^T K x over the ranks once
+// every compute CTA has contributed.  Nothing of the exchange is left on the critical path but the last flag wait.
+struct HaloArgs {
+  double* mb;                       // this rank's mailbox, the lower / upper neighbour's (nullptr at the ends)
+  double* lo;
+  double* hi;
+  exab_p2p::PeerTable peers;
+  int rank, nranks, ncomm;
+  long nn, plane;
+  long nb_lo, nb_hi, hi_start;      // boundary warp tiles: [0, nb_lo) and [hi_start, hi_start + nb_hi)
+  unsigned long long seq_halo, seq_scal;
+  unsigned long long* counters;     // [0] boundary tiles done, [1] compute CTAs done (both cumulative over launches)
+  unsigned long long tiles_target, ctas_target;
+};
+
 // register cap: 12 resident warps per SM (6 CTAs of 2 warps, 3 of 4, 12 of 1)
-template <int NW, int STAGES, bool ESS>
+template <int NW, int STAGES, bool ESS, bool HALO = false>
 __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __grid_constant__ CUtensorMap tmap,
                                                             const double* __restrict__ x, double* __restrict__ y,
                                                             ElemIO io, long nelems, double dt,
                                                             double* __restrict__ dot_accum,
-                                                            const double* __restrict__ xend) {
+                                                            const double* __restrict__ xend,
+                                                            const __grid_constant__ HaloArgs h) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ncomm = HALO ? h.ncomm : 0;
+  if (HALO && (int)blockIdx.x < ncomm) {
+    __shared__ bool s_ok;
+    if (threadIdx.x == 0)
+      while (exab_p2p::ld_acquire_gpu(&h.counters[0]) < h.tiles_target) __nanosleep(200);
+    __syncthreads();
+    exab_p2p::halo_exchange_blocks(y, h.mb, h.lo, h.hi, h.nn, h.plane, h.seq_halo, h.peers.spin_limit, blockIdx.x,
+                                   (unsigned)ncomm, &s_ok);
+    if (blockIdx.x == 0 && dot_accum) {
+      if (threadIdx.x == 0)
+        while (exab_p2p::ld_acquire_gpu(&h.counters[1]) < h.ctas_target) __nanosleep(200);
+      __syncthreads();
+      if (threadIdx.x < 32) exab_p2p::warp_allreduce_p2p(dot_accum, h.peers, h.rank, h.nranks, 1, h.seq_scal, threadIdx.x);
+    }
+    return;
+  }
   // warp index through a broadcast: tells the compiler it is warp-uniform (uniform loop bounds, no re-convergence
   // barriers around the shuffles)
   const int w = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0), l32 = threadIdx.x & 31;
@@ -411,9 +449,17 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
   unsigned char* ring = base + (size_t)w * STAGES * kWarpStageBytesC;
   uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)NW * STAGES * kWarpStageBytesC) + w * STAGES;
   const long nwt = (nelems + 3) >> 2;  // warp tiles of 4 elements = 32 points
-  const long stride = (long)gridDim.x * NW;
-  const long wt0 = (long)blockIdx.x * NW + w;
+  const long stride = (long)(gridDim.x - ncomm) * NW;
+  const long wt0 = (long)(blockIdx.x - ncomm) * NW + w;   // first ITERATION index of this warp
   const uint64_t pol = l2_policy_evict_first();
+  // iteration index -> warp tile: identity, or boundary layers first (HALO)
+  const long nb_lo = HALO ? h.nb_lo : 0, nb_hi = HALO ? h.nb_hi : 0, nb = nb_lo + nb_hi;
+  auto tile_of = [&](long it) -> long {
+    if (!HALO) return it;
+    if (it < nb_lo) return it;
+    if (it < nb) return h.hi_start + (it - nb_lo);
+    return it - nb_hi;
+  };
 
   if (l32 == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
@@ -432,12 +478,13 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
   {
     long t = wt0;
     for (int s = 0; s < STAGES; ++s, t += stride)
-      if (t < nwt) issue(t, s);
+      if (t < nwt) issue(tile_of(t), s);
   }
 
-  auto load_nid = [&](long wt) -> int {
-    const long e = (wt << 2) + el;
-    if (wt >= nwt || e >= nelems) return -1;
+  auto load_nid = [&](long it) -> int {
+    if (it >= nwt) return -1;
+    const long e = (tile_of(it) << 2) + el;
+    if (e >= nelems) return -1;
     return io.e2n[e * 8 + lex_to_native(lane)];
   };
   auto load_x = [&](int nid, unsigned& msk, double& x0, double& x1, double& x2, double& c0, double& c1, double& c2) {
@@ -521,7 +568,7 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
       const long tnext = wt + (long)STAGES * stride;
       if (tnext < nwt) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(tnext, s);
+        issue(tile_of(tnext), s);
       }
     }
     const double y0 = qp_grad_to_nodal(t00, t10, t20, sg);
@@ -533,6 +580,11 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
       if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
       if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], y2);
     }
+    if (HALO && wt < nb) {  // a boundary-layer tile is complete: count it off for the exchange CTAs
+      __threadfence();
+      __syncwarp();
+      if (l32 == 0) atomicAdd(&h.counters[0], 1ull);
+    }
     nid_c = nid_n; nid_n = nid_n2;
     msk_c = msk_n; xc0 = xn0; xc1 = xn1; xc2 = xn2;
     cc0 = cn0; cc1 = cn1; cc2 = cn2;
@@ -542,6 +594,11 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) xdoty += __shfl_xor_sync(kFull, xdoty, m);
     if (l32 == 0) red_add_f64(dot_accum, xdoty);
+  }
+  if (HALO) {  // this CTA's share of x^T K x is in: CTA 0 all-reduces once every compute CTA has said so
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&h.counters[1], 1ull);
   }
 }
 

@@ -122,6 +122,29 @@ enum { EXAB200_LOCAL_ACTION = 1, EXAB200_NO_ZERO = 2 };
 int exab200_grad_mult_ex(exab200_ctx* ctx, const double* d_x_L, double* d_y_L, int flags, double* d_dot_accum,
                          void* stream);
 
+/* The same operator for one z-slab of a multi-GPU run, WITH what ParNonlinearForm wraps around it in the reference
+ * (P^T ... P: the shared-dof sum, src/mechanics_operator_ext.cpp:149,157) and the all-reduce of the fused CG
+ * denominator -- one kernel over NVLink peer memory: the two boundary element layers are processed first, a few CTAs
+ * push their interface-plane sums into the neighbours' mailboxes and add the neighbours' while the interior streams,
+ * and *d_dot_accum ends up summed over all ranks.  Mailboxes are CUDA-IPC mapped buffers laid out as documented in
+ * exaconstit_b200/csrc/exab200_p2p.cuh; seq_halo / seq_scal are the caller's monotonically increasing sequence
+ * numbers of that protocol.  exab200_grad_mult_halo_supported() tells whether the context can use it (PA with compact
+ * tangent records, >= 3 element layers); otherwise call exab200_grad_mult_ex and exchange separately. */
+typedef struct exab200_halo {
+  double* mailbox;           /* this rank's mailbox (device) */
+  double* lo;                /* lower / upper z-neighbour's mailbox, NULL at the ends of the rank line */
+  double* hi;
+  double* peers[8];          /* every rank's mailbox (scalar all-reduce) */
+  long long spin_limit;      /* clock64 ticks before a lost peer is reported instead of waited for */
+  int rank, nranks;
+  long plane;                /* nodes per interface plane */
+  long layer_elems;          /* elements per z-layer; elements are ordered layer by layer */
+  unsigned long long seq_halo, seq_scal;
+} exab200_halo;
+int exab200_grad_mult_halo_supported(exab200_ctx* ctx, const exab200_halo* h);
+int exab200_grad_mult_halo(exab200_ctx* ctx, const double* d_x_L, double* d_y_L, int flags, double* d_dot_accum,
+                           const exab200_halo* h, void* stream);
+
 /* AssembleGradDiagonalPA / EA AssembleDiagonal (src/mechanics_integrators.cpp:625-748,1607-1805;
  * src/mechanics_operator_ext.cpp:95-123,228-265).  L form: diag[ess] = 1. */
 int exab200_grad_diag_evec(exab200_ctx* ctx, double* d_diag_E, void* stream);

@@ -41,10 +41,15 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("p2p,case", [(0, "voce_pa"), (1, "voce_pa"), (1, "voce_full_cyclic_csm")])
-def test_two_rank_run_matches_single_rank(tmp_path, p2p, case):
+@pytest.mark.parametrize("p2p,case,env", [(0, "voce_pa", {}), (1, "voce_pa", {}), (1, "voce_full_cyclic_csm", {}),
+                                          (1, "voce_pa", {"EXAHOST_NO_HALO_FUSION": "1"}),
+                                          (1, "voce_pa", {"EXAHOST_NO_HALO_FUSION": "1", "EXAHOST_NO_CG_FUSION": "1"}),
+                                          (1, "voce_pa", {"EXAB200_HALO_CTAS": "3"})],
+                         ids=["nccl", "p2p", "p2p-vgrad", "p2p-separate-halo-kernel", "p2p-separate-kernels", "p2p-3-exchange-ctas"])
+def test_two_rank_run_matches_single_rank(tmp_path, p2p, case, env):
     """voce_pa: velocity BCs; voce_full_cyclic_csm: velocity-gradient BCs mixed with a velocity BC (the origin of the
-    velocity gradient is a MIN over the ranks' coordinates)"""
+    velocity gradient is a MIN over the ranks' coordinates).  Default peer-memory path = operator apply with the
+    interface exchange folded in + one-launch CG vector update; the environment switches select the separate kernels."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -52,8 +57,8 @@ def test_two_rank_run_matches_single_rank(tmp_path, p2p, case):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % dict(root=ROOT, nsteps=nsteps, p2p=p2p, case=case))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", str(29611 + p2p + 2 * (case != "voce_pa")), str(script)],
-                         capture_output=True, text=True, timeout=600)
+                          "--master-addr", "127.0.0.1", "--master-port", str(29611 + p2p + 2 * (case != "voce_pa") + 4 * len(env)), str(script)],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")][-1]
     res = json.loads(line[7:])
