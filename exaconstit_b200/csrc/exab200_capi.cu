@@ -59,7 +59,7 @@ struct exab200_ctx {
   // operator apply with the interface-plane exchange folded in (exab200_grad_mult_halo)
   unsigned long long* d_halo_cnt = nullptr;
   unsigned long long halo_tiles_cum = 0, halo_ctas_cum = 0;
-  int halo_ctas = 8;
+  int halo_ctas = 16;  // exchange CTAs of the fused kernel (B200, 8 ranks: 8 -> 137 us, 16 -> 115 us per apply with 4-deep loads)
   int variant_ea = 40, ctas_ea = 3;
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };

@@ -83,16 +83,17 @@ __device__ __forceinline__ void halo_exchange_blocks(double* __restrict__ v, dou
                                                      bool* s_ok) {
   const int par = (int)(seq & 1);
   const long n3 = 3 * plane, top = nn - plane;
-  // four independent elements per thread and pass: the exchange blocks are few (latency-bound loads)
+  // kU independent elements per thread and pass: the exchange blocks are few (latency-bound loads)
+  constexpr int kU = 8;
   const long step = (long)nblk * blockDim.x, first = (long)blk * blockDim.x + threadIdx.x;
   for (int c = 0; c < 3; ++c) {
     const long vo = c * nn, mo = c * plane;
     double* dlo = lo ? lo + kMbHalo + (2 + par) * n3 + mo : nullptr;
     double* dhi = hi ? hi + kMbHalo + (0 + par) * n3 + mo : nullptr;
-    for (long n = first; n < plane; n += 4 * step) {
-      double a[4], b[4];
+    for (long n = first; n < plane; n += kU * step) {
+      double a[kU], b[kU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const long m = n + u * step;
         if (m < plane) {
           if (lo) a[u] = ld_cg(&v[vo + m]);
@@ -100,7 +101,7 @@ __device__ __forceinline__ void halo_exchange_blocks(double* __restrict__ v, dou
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const long m = n + u * step;
         if (m < plane) {
           if (lo) dlo[m] = a[u];
@@ -131,10 +132,10 @@ __device__ __forceinline__ void halo_exchange_blocks(double* __restrict__ v, dou
     const long vo = c * nn, mo = c * plane;
     const double* slo = mb + kMbHalo + (0 + par) * n3 + mo;
     const double* shi = mb + kMbHalo + (2 + par) * n3 + mo;
-    for (long n = first; n < plane; n += 4 * step) {
-      double a[4], b[4];
+    for (long n = first; n < plane; n += kU * step) {
+      double a[kU], b[kU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const long m = n + u * step;
         if (m < plane) {
           if (lo) a[u] = ld_cg(&v[vo + m]) + ld_cg(&slo[m]);
@@ -142,7 +143,7 @@ __device__ __forceinline__ void halo_exchange_blocks(double* __restrict__ v, dou
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const long m = n + u * step;
         if (m < plane) {
           if (lo) v[vo + m] = a[u] + poison;
