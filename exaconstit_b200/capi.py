@@ -24,7 +24,8 @@ SYMBOLS = [
     "exab200_num_state_vars", "exab200_set_essential_mask", "exab200_hist_init",
     "exab200_setup_jacobians", "exab200_model_setup", "exab200_model_setup_evec",
     "exab200_failed_points", "exab200_residual_evec", "exab200_residual", "exab200_grad_setup",
-    "exab200_grad_mult_evec", "exab200_grad_mult", "exab200_grad_mult_ex", "exab200_grad_diag_evec", "exab200_grad_diag",
+    "exab200_grad_mult_evec", "exab200_grad_mult", "exab200_grad_mult_ex", "exab200_grad_mult_halo_supported",
+    "exab200_grad_mult_halo", "exab200_grad_diag_evec", "exab200_grad_diag",
     "exab200_ea_assemble", "exab200_ea_mult_evec", "exab200_vol_sum", "exab200_calc_dp",
     "exab200_grad_calc", "exab200_launch_count", "exab200_set_tuning", "exab200_set_tangent_format",
 ]

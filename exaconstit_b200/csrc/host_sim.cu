@@ -541,7 +541,7 @@ class SlabComm {
       const long long ticks = (long long)(std::atof(e) * 2.0e9);
       if (ticks > 0) peers.spin_limit = ticks;
     }
-    n_owned = (rank == nranks - 1) ? nn : nn - plane;
+    n_owned = (rank == nranks - 1) ? nn : nn - plane;  // = exahost_slab_layout out[4] (checked by exahost_create)
     partial.SetSize(kRedBlocks);
     scal.SetSize(8);
     counter.SetSize(2);
@@ -1180,6 +1180,22 @@ extern "C" {
 
 const char* exahost_last_error(void) { return g_err.c_str(); }
 
+int exahost_slab_layout(int nx, int ny, int nz_total, int rank, int nranks, long* out) {
+  if (nx < 1 || ny < 1 || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks || nz_total < nranks) {
+    g_err = "exahost_slab_layout: need nx, ny >= 1, 1 <= nranks <= 8, 0 <= rank < nranks and at least one element layer per rank";
+    return 1;
+  }
+  const long base = nz_total / nranks, rem = nz_total % nranks;      // the first `rem` ranks take one layer more
+  const long z0 = rank * base + std::min<long>(rank, rem), nzl = base + (rank < rem ? 1 : 0);
+  const long plane = (long)(nx + 1) * (ny + 1), nn = plane * (nzl + 1), layer = (long)nx * ny, ne = layer * nzl;
+  out[0] = z0; out[1] = nzl; out[2] = nn; out[3] = plane;
+  out[4] = (rank == nranks - 1) ? nn : nn - plane;
+  out[5] = 0; out[6] = nn - plane;
+  out[7] = ne; out[8] = rank > 0; out[9] = rank < nranks - 1;
+  out[10] = (layer + 3) / 4; out[11] = (ne - layer) / 4;
+  return 0;
+}
+
 int exahost_nccl_unique_id(void* out128) {
   if (!g_nccl.load()) { g_err = "NCCL library could not be loaded"; return 1; }
   ncclUniqueId id;
@@ -1196,6 +1212,9 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
     HCK(cudaSetDevice(cfg->device));
     HCK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     const long nx = cfg->nx, ny = cfg->ny, nzl = cfg->nz_local;
+    long lay[12];
+    if (exahost_slab_layout(cfg->nx, cfg->ny, cfg->nz_total, cfg->rank, cfg->nranks, lay)) throw Abort{g_err};
+    if (lay[0] != cfg->z0 || lay[1] != nzl) throw Abort{"exahost_create: (z0, nz_local) is not this rank's slab of exahost_slab_layout"};
     s->nelems = nx * ny * nzl;
     s->plane = (nx + 1) * (ny + 1);
     s->nnodes = s->plane * (nzl + 1);
@@ -1258,6 +1277,7 @@ int exahost_create(const exahost_config* cfg, exahost_sim** out) {
       HCK(cudaStreamSynchronize(s->stream));
     }
     s->comm.Init(cfg->rank, cfg->nranks, cfg->nccl_id, s->stream, s->nnodes, s->plane);
+    if (s->comm.n_owned != lay[4] || s->nnodes != lay[2] || s->nelems != lay[7]) throw Abort{"slab layout mismatch"};
     const Assembly as = cfg->assembly == EXAB200_EA ? Assembly::EA : Assembly::PA;
     s->model.reset(new ExaCMechModel(s->ctx, s->stream, &s->stress0, &s->stress1, &s->matGrad, &s->matVars0, &s->matVars1,
                                      cfg->nprops, as));

@@ -55,6 +55,18 @@ def nccl_unique_id():
     return bytes(buf)
 
 
+_LAYOUT_KEYS = ("z0", "nz_local", "nnodes", "plane", "n_owned", "lo_offset", "hi_offset", "nelems", "has_lo", "has_hi",
+                "lo_tiles", "hi_tile_start")
+
+
+def slab_layout(nx, ny, nz, rank, nranks):
+    """exahost_slab_layout: this rank's z-slab of the voxel mesh and the ownership / interface-plane index sets of the
+    exchanges (the C++ host layer's own partition arithmetic; no device needed)."""
+    out = (C.c_long * 12)()
+    _chk(lib().exahost_slab_layout(nx, ny, nz, rank, nranks, out))
+    return dict(zip(_LAYOUT_KEYS, [int(v) for v in out]))
+
+
 class VoxelSim:
     """One rank's slab of a voxel-mesh simulation.  `n` = (nx, ny, nz_total); with nranks > 1 the element
     layers are split by voxel.slab_partition and `grain_ids` is the GLOBAL x-fastest array."""
@@ -63,8 +75,8 @@ class VoxelSim:
                  nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, 1000), true_jacobi=False, rank=0, nranks=1, device=0,
                  nccl_id=None, verbose=0):
         nx, ny, nz = n
-        z0s = voxel.slab_partition(nz, nranks)
-        self.z0, self.nzl = int(z0s[rank]), int(z0s[rank + 1] - z0s[rank])
+        lay = slab_layout(nx, ny, nz, rank, nranks)
+        self.z0, self.nzl = lay["z0"], lay["nz_local"]
         self.nx, self.ny, self.nz = nx, ny, nz
         self.rank, self.nranks = rank, nranks
         self.nelems = nx * ny * self.nzl

@@ -37,6 +37,16 @@ typedef struct {
   int verbose;
 } exahost_config;
 
+/* z-slab element partition of an nx*ny*nz_total voxel mesh over `nranks` ranks and the ownership / interface-plane
+ * index sets the exchanges work with (host arithmetic only; exahost_create validates its config against it and the
+ * exchange kernels index with the same numbers):
+ *   out[0] z0 (first element layer)   out[1] nz_local           out[2] local nodes (both interface planes included)
+ *   out[3] nodes per plane            out[4] uniquely-owned nodes (all but the top plane; the last rank owns it too)
+ *   out[5] node offset of the bottom interface plane in the local L-vector components, out[6] of the top one
+ *   out[7] local elements             out[8] has lower neighbour  out[9] has upper neighbour
+ *   out[10] leading warp tiles (4 elements) of the bottom layer   out[11] first warp tile of the top layer
+ * returns 0, or 1 for an impossible layout (fewer layers than ranks, nranks outside 1..8). */
+int exahost_slab_layout(int nx, int ny, int nz_total, int rank, int nranks, long* out12);
 const char* exahost_last_error(void);
 int exahost_nccl_unique_id(void* out128);
 int exahost_create(const exahost_config* cfg, exahost_sim** out);

@@ -1,27 +1,27 @@
-"""Host-side logic of the z-slab element partition used across GPUs (one process per GPU).
+"""Test harness for the z-slab exchange semantics (world-size-2 gloo runs on CPU, tests/test_parallel_gloo.py).
 
-The C++ `SlabComm` (csrc/host_sim.cu) implements these semantics with NCCL on device buffers; this
-module states them with `torch.distributed` tensors so they can be exercised with the gloo backend on
-CPU (world_size 2) and so that Python-side drivers can scatter/gather global fields.
+The partition, ownership and interface-plane index sets come from the C++ host layer itself (exahost_slab_layout,
+csrc/host_sim.cu: the numbers exahost_create sizes its vectors with and the exchange kernels index with); this module
+only states the two exchanges -- interface-plane sum with the z-neighbours, owned-dof dot product -- with
+`torch.distributed` tensors so that they can be exercised without GPUs and compared with the single-domain oracle.
 
-Layout: rank r owns element layers [z0[r], z0[r+1]) and keeps a local byNODES L-vector over node planes
-z0[r] .. z0[r+1] (both interface planes included).  Uniquely-owned dofs = all local nodes except the top
-plane (the last rank owns its top plane too)."""
+Layout: rank r owns element layers [z0, z0 + nz_local) and keeps a local byNODES L-vector over node planes
+z0 .. z0 + nz_local (both interface planes included).  Uniquely-owned dofs = all local nodes except the top plane
+(the last rank owns its top plane too)."""
 import numpy as np
 
-from . import voxel
+from exaconstit_b200 import host
 
 
 class SlabLayout:
     def __init__(self, nx, ny, nz, rank, nranks):
         self.nx, self.ny, self.nz, self.rank, self.nranks = nx, ny, nz, rank, nranks
-        z0s = voxel.slab_partition(nz, nranks)
-        self.z0, self.z1 = int(z0s[rank]), int(z0s[rank + 1])
-        self.nzl = self.z1 - self.z0
-        self.plane = (nx + 1) * (ny + 1)
-        self.nnodes = self.plane * (self.nzl + 1)
-        self.nelems = nx * ny * self.nzl
-        self.n_owned = self.nnodes if rank == nranks - 1 else self.nnodes - self.plane
+        lay = host.slab_layout(nx, ny, nz, rank, nranks)
+        self.z0, self.nzl = lay["z0"], lay["nz_local"]
+        self.z1 = self.z0 + self.nzl
+        self.plane, self.nnodes, self.nelems, self.n_owned = lay["plane"], lay["nnodes"], lay["nelems"], lay["n_owned"]
+        self.lo_offset, self.hi_offset = lay["lo_offset"], lay["hi_offset"]
+        self.has_lo, self.has_hi = bool(lay["has_lo"]), bool(lay["has_hi"])
         self.nn_global = self.plane * (nz + 1)
 
     # ---- global <-> local field maps (byNODES L-vectors, x-fastest element arrays) ----
@@ -35,7 +35,7 @@ class SlabLayout:
 
     def plane_slices(self, which):
         """Index arrays (into the local L-vector) of the bottom ('lo') or top ('hi') interface plane."""
-        off = 0 if which == "lo" else self.nnodes - self.plane
+        off = self.lo_offset if which == "lo" else self.hi_offset
         return np.concatenate([c * self.nnodes + off + np.arange(self.plane) for c in range(3)])
 
     # ---- exchanges, stated with torch.distributed (any backend) ----
@@ -44,7 +44,7 @@ class SlabLayout:
         import torch
         if self.nranks == 1:
             return v
-        lo, hi = self.rank > 0, self.rank < self.nranks - 1
+        lo, hi = self.has_lo, self.has_hi
         ilo, ihi = torch.as_tensor(self.plane_slices("lo")), torch.as_tensor(self.plane_slices("hi"))
         reqs, rlo, rhi = [], None, None
         if lo:

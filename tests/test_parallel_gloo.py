@@ -1,5 +1,6 @@
-"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: slab partition, ownership, interface-plane
-sums and owned-dof dot products, checked against the single-domain oracle operator."""
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: the C++ host layer's slab partition, ownership and
+interface-plane index sets (exahost_slab_layout) driving interface-plane sums and owned-dof dot products over
+torch.distributed, checked against the single-domain oracle operator."""
 import os
 
 import numpy as np
@@ -16,7 +17,9 @@ def _worker(rank, world, port, q):
         import sys
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         sys.path.insert(0, root)
-        from exaconstit_b200 import parallel, voxel
+        sys.path.insert(0, os.path.join(root, "tests"))
+        from exaconstit_b200 import voxel
+        import slab_exchange as parallel
         from oracle import orc
         n = (4, 3, 5)
         nx, ny, nz = n
@@ -79,13 +82,25 @@ def test_slab_exchange_world2(orc):
 
 
 def test_slab_partition_covers_mesh():
-    from exaconstit_b200 import parallel, voxel
-    for nz, nr in [(5, 2), (128, 8), (7, 3), (4, 4)]:
+    from exaconstit_b200 import host, voxel
+    import slab_exchange as parallel
+    for nz, nr in [(5, 2), (128, 8), (7, 3), (4, 4), (130, 8)]:
         z0 = voxel.slab_partition(nz, nr)
         assert z0[0] == 0 and z0[-1] == nz and np.all(np.diff(z0) >= 1)
         lays = [parallel.SlabLayout(3, 2, nz, r, nr) for r in range(nr)]
+        assert [l.z0 for l in lays] == [int(z) for z in z0[:-1]] and lays[-1].z1 == nz     # C++ and Python partitions agree
         assert sum(l.nelems for l in lays) == 3 * 2 * nz
         assert sum(l.n_owned for l in lays) == 4 * 3 * (nz + 1)
+        for r, l in enumerate(lays):
+            assert l.has_lo == (r > 0) and l.has_hi == (r < nr - 1)
+            assert l.lo_offset == 0 and l.hi_offset == l.nnodes - l.plane
+            lay = host.slab_layout(3, 2, nz, r, nr)
+            # the operator kernel's boundary-first order: leading tiles cover the bottom layer, the tail the top layer
+            assert lay["lo_tiles"] * 4 >= 6 and lay["hi_tile_start"] * 4 <= l.nelems - 6
+    with pytest.raises(host.HostError):
+        host.slab_layout(3, 2, 4, 0, 9)          # more ranks than one NVLink box holds
+    with pytest.raises(host.HostError):
+        host.slab_layout(3, 2, 2, 0, 4)          # fewer layers than ranks
 
 
 def test_slab_bc_masks_tile_the_global_masks():
