@@ -47,6 +47,39 @@ PROPS_VOCE = [8.920e-6, 0.003435984, 1.0e-10, 168.4, 121.4, 75.2, 44.0, 0.02, 1.
 BC = ([1, 2, 3, 4], [3, 1, 2, 3], [[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0.001]])
 ALG_BYTES_PA_APPLY = 3264      # per element
 ALG_BYTES_QPT_UPDATE = 928     # per quadrature point
+ALG_BYTES_EA_APPLY = 4992      # per element (576 + 24 + 24 doubles)
+ALG_BYTES_QPT_UPDATE_HCP = 1120
+
+# Synthetic HCP (Ti-like) KMBalD property vector for BASELINE.json configs[4].  The reference ships NO hcp property
+# set, so these values are ours and HCP results are parity-unpinned against the reference (GPU vs
+# oracle only).  Order: rho0, cv, tol | c11 c12 c13 c33 c44 | mu_ref, T_ref | c_1 x4 slip families (basal, prismatic,
+# pyramidal<a>, pyramidal<c+a>) | tau_a, p, q | gam_wo, gam_ro, wrD | g_0 x4 | s x4 | k1, k2_0, n^-1, gamma_o,
+# rho_dd_ref | c/a | Gruneisen, e_ref
+_CV_HCP = 2.5e-3
+PROPS_HCP = [4.5e-6, _CV_HCP, 1.0e-10, 162.4, 92.0, 69.0, 180.7, 46.7, 44.0, 300.0, 1944.1, 1944.1, 2100.0, 2400.0,
+             4.0e-4, 1.0, 1.0, 1.0, 1.0, 3.0e-2, 8.0e-3, 6.0e-3, 1.2e-2, 2.0e-2, 1.0e-1, 1.0e-1, 1.2e-1, 1.5e-1,
+             3.0e-4, 5.0e-5, 0.1, 1.0e-2, 9.0e-4, 1.587, 0.0, -_CV_HCP * 300.0]
+
+
+def bench_config(which, krylov_iter):
+    """The two bench lines: 4 = BASELINE.json configs[3] (the headline: FCC Voce, PA + PCG), 5 = configs[4] (HCP KMBalD,
+    B-bar + EA + NRLS, cyclic loading: workflows/Stage3/common_simulation_files/options_master.toml:83-106 with the load
+    reversals of test/data/voce_full_cyclic.toml:45-74)."""
+    if which == 5:
+        rev = {1: 1.0, 11: -1.0, 31: 1.0, 51: -1.0, 71: 1.0}
+        return dict(name="HCP KMBalD (synthetic Ti-like set), B-bar + EA + PCG (identity smoother, %d-iter cap), Newton with "
+                         "line search, cyclic uniaxial velocity BC" % krylov_iter,
+                    xtal=2, kin=2, props=PROPS_HCP, assembly=1, integ=1, nl_solver=1, nr=(5e-5, 5e-10, 25),
+                    kr=(1e-7, 1e-27, krylov_iter), dts=lambda nsteps: [0.1] * nsteps,
+                    bc_at=lambda step: (BC[0], BC[1], [[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0.001 * rev[step]]]) if step in rev else None,
+                    alg_bytes=ALG_BYTES_EA_APPLY, alg_qpt=ALG_BYTES_QPT_UPDATE_HCP,
+                    kernel="k_ea_mult_p<2,2,ESS> (EA gradient apply: lane-interleaved element matrices via bulk TMA)")
+    return dict(name="FCC Voce, PA + PCG (identity smoother, %d-iter cap), uniaxial velocity BC" % krylov_iter,
+                xtal=0, kin=0, props=PROPS_VOCE, assembly=0, integ=0, nl_solver=0, nr=(5e-5, 5e-10, 25),
+                kr=(1e-7, 1e-27, krylov_iter), dts=dt_schedule, bc_at=lambda step: BC if step == 1 else None,
+                alg_bytes=ALG_BYTES_PA_APPLY, alg_qpt=ALG_BYTES_QPT_UPDATE,
+                kernel="k_grad_mult_pa_c<2,2,ESS> (PA gradient apply: compact tangent records via tiled TMA, Jacobians "
+                       "rebuilt from coordinates)")
 
 
 def peaks():
@@ -134,19 +167,32 @@ def run_ours(args):
     ngrains, seed = grains_for(n, args.grains)
     nz = args.nz or n
     grains, quats = workload(n, ngrains, seed, nz)
-    sim = host.VoxelSim((n, n, nz), (1.0, 1.0, nz / n), 0, 0, PROPS_VOCE, 298.0, grains, quats, assembly=0,
-                        nr=(5e-5, 5e-10, 25), kr=(1e-7, 1e-27, args.krylov_iter), true_jacobi=args.true_jacobi,
-                        rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
+    cfg = bench_config(args.config, args.krylov_iter)
+    sim = host.VoxelSim((n, n, nz), (1.0, 1.0, nz / n), cfg["xtal"], cfg["kin"], cfg["props"], 298.0, grains, quats,
+                        assembly=cfg["assembly"], integ=cfg["integ"], nl_solver=cfg["nl_solver"], nr=cfg["nr"], kr=cfg["kr"],
+                        true_jacobi=args.true_jacobi, rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
     if nranks > 1 and not args.nccl_only:
         sim.enable_peer_collectives(dist)
     for tv in args.tuning:
         c, v = tv.split(":")
         sim.set_tuning(int(c), int(v))
-    bc = BC
-    if nz != n:  # slab diagnostic: same axial strain rate as the cube
-        bc = (BC[0], BC[1], [[v * nz / n for v in row] for row in BC[2]])
-    mask, ess_val = sim.set_bcs(*bc)
-    ess_pinned = np.ascontiguousarray(ess_val)
+    state = {"ess": None}
+
+    def apply_bcs(step):
+        """UpdateEssBdr at the steps the configuration changes its BCs (1-based); returns True if they changed"""
+        bc = cfg["bc_at"](step)
+        if bc is None:
+            return False
+        if nz != n:  # slab diagnostic: same axial strain rate as the cube
+            bc = (bc[0], bc[1], [[v * nz / n for v in row] for row in bc[2]])
+        _, ess_val = sim.set_bcs(*bc)
+        state["ess"] = np.ascontiguousarray(ess_val)
+        return True
+
+    def do_step(i):
+        changed = apply_bcs(i + 1)
+        return sim.step(dts[i], bc_changed=changed, ess_val_host=state["ess"], vel_out_host=vel_out)
+
     vel_out = np.zeros(3 * sim.nnodes)
 
     def barrier():
@@ -156,9 +202,9 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     steps = []
-    dts = dt_schedule(args.warmup + args.steps)
+    dts = cfg["dts"](args.warmup + args.steps)
     for i in range(args.warmup):
-        steps.append(sim.step(dts[i], bc_changed=(i == 0), ess_val_host=ess_pinned, vel_out_host=vel_out))
+        steps.append(do_step(i))
         if not steps[-1]["converged"]:
             raise SystemExit("bench.py: Newton did not converge in warm-up step %d" % (i + 1))
     sim.kernel_timing(True)
@@ -172,7 +218,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     timed = []
     for i in range(args.warmup, args.warmup + args.steps):
-        timed.append(sim.step(dts[i], bc_changed=(i == 0), ess_val_host=ess_pinned, vel_out_host=vel_out))
+        timed.append(do_step(i))
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -193,33 +239,35 @@ def run_ours(args):
     peak, peak_src = peaks()
     if rank == 0:
         apply_ms = gm_ms / max(gm_cnt, 1)
-        achieved = ne_local * ALG_BYTES_PA_APPLY / (apply_ms * 1e-3) / 1e9 if gm_cnt else None
+        traffic, traffic_src = ncu_traffic(args.config, ne_local)
+        achieved = ne_local * cfg["alg_bytes"] / (apply_ms * 1e-3) / 1e9 if gm_cnt else None
         k1_ms = ms_ms / max(ms_cnt, 1)
         out = {
             "metric": "newton_steps_per_sec", "value": newton / (dev_ms * 1e-3), "unit": "Newton-steps/s",
             "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_FMT % (n, ngrains, args.krylov_iter),
+            "config": {"workload": "%d^3 voxel, %d Voronoi grains, %s" % (n, ngrains, cfg["name"]), "baseline_config": args.config,
                        "mesh": [n, n, nz], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi),
                        "cache": "inputs >> L2 (%.1f GB of quadrature data per rank)" % (ne_local * 8 * (36 + 9 + 2 * 28 + 12) * 8 / 1e9),
                        "newton_iters": newton, "pcg_iters": pcg, "model_setups": setups, "grad_mults": gmults},
             "e2e": {"value": newton / (e2e_ms * 1e-3), "unit": "Newton-steps/s",
-                    "h2d_bytes_per_step": int(ess_pinned.nbytes), "d2h_bytes_per_step": int(vel_out.nbytes + 7 * 8)},
+                    "h2d_bytes_per_step": int(state["ess"].nbytes), "d2h_bytes_per_step": int(vel_out.nbytes + 7 * 8)},
             "gpu_launches": int(launches),
             "qpt_updates_per_sec": (ne_local * 8 * nranks) / (k1_ms * 1e-3) if ms_cnt else None,
             "pa_mult_GBps_per_gpu": achieved,
-            "roofline": {"kernel": "k_grad_mult_pa_c<2,2,ESS> (PA gradient apply: compact tangent records via tiled TMA, Jacobians rebuilt from coordinates)", "bound": "hbm",
+            "roofline": {"kernel": cfg["kernel"], "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": TRAFFIC_NCU.get(n) if nranks == 1 else None,
-                         "algorithmic_bytes_per_launch": ne_local * ALG_BYTES_PA_APPLY,
+                         "traffic": traffic,
+                         "algorithmic_bytes_per_launch": ne_local * cfg["alg_bytes"],
                          # the same launch time against the bytes the kernel really moves (ncu): the algorithmic figure
                          # counts the 36-entry tangent and the Jacobians, which the default kernel no longer reads
-                         "dram_frac": (TRAFFIC_NCU[n] / (apply_ms * 1e-3) / 1e9 / peak) if (nranks == 1 and n in TRAFFIC_NCU and gm_cnt) else None,
+                         "dram_frac": (traffic / (apply_ms * 1e-3) / 1e9 / peak) if (traffic and gm_cnt) else None,
+                         "traffic_source": traffic_src,
                          "launches_timed": int(gm_cnt), "avg_launch_ms": apply_ms,
                          "share_of_step": gm_ms / dev_ms},
             "model_setup": {"avg_ms": k1_ms, "calls": int(ms_cnt), "share_of_step": ms_ms / dev_ms,
-                            "GBps_algorithmic": ne_local * 8 * ALG_BYTES_QPT_UPDATE / (k1_ms * 1e-3) / 1e9 if ms_cnt else None},
+                            "GBps_algorithmic": ne_local * 8 * cfg["alg_qpt"] / (k1_ms * 1e-3) / 1e9 if ms_cnt else None},
             "clocks": clocks,
             "avg_stress_zz_last": float(timed[-1]["avg_stress"][2]),
             "all_steps_converged": bool(all(s["converged"] for s in timed)),
@@ -230,12 +278,12 @@ def run_ours(args):
                              "other": 1.0 - (gm_ms + ms_ms) / dev_ms, "us_per_pcg_iteration": dev_ms * 1e3 / max(pcg, 1),
                              "us_per_pcg_iteration_outside_k1": (dev_ms - ms_ms) * 1e3 / max(pcg, 1)},
         }
-        if nranks == 1 and not args.no_cpu_baseline:
+        if nranks == 1 and not args.no_cpu_baseline and args.config == 4:
             out["cpu_baseline"] = cpu_baseline(n, args.krylov_iter, args.warmup, budget_s=args.cpu_budget)
         out["parity_fingerprint"] = check_fingerprint(n, ngrains, args, steps + timed)
         sim.close()
         sim = None
-        if nranks == 1 and not args.no_same_config:
+        if nranks == 1 and not args.no_same_config and args.config == 4:
             # the same time steps on the sample meshes the CPU arm may pick: an un-extrapolated GPU/CPU pair
             # (compare with the reference arm's config.newton_steps_per_sec_on_sample at its config.sample_mesh)
             out["config"]["newton_steps_per_sec_on_sample_meshes"] = {
@@ -288,11 +336,18 @@ def check_fingerprint(n, ngrains, args, steps):
             "newton_iters_identical": bool(newton_same), "stored_run": fp[key].get("run", "1 GPU")}
 
 
-# ncu --set full dram bytes (read+write) per K2 launch, filled in from profiles/ (see profiles/README.md)
-TRAFFIC_NCU = {}
-_tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
-if os.path.exists(_tp):
-    TRAFFIC_NCU = {int(k): v for k, v in json.load(open(_tp)).items()}
+def ncu_traffic(config, nelems_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set
+    full` captures (profiles/k2_traffic.json: bytes per element by configuration and shard size; see profiles/README.md for
+    the build they were taken on).  None if no capture covers this shard size."""
+    p = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p))
+    ent = t.get("config%d" % config, {}).get(str(nelems_local))
+    if not ent:
+        return None, None
+    return ent["dram_bytes_per_launch"], ent.get("source")
 
 
 WORKLOAD_FMT = ("%d^3 voxel, %d Voronoi grains, FCC Voce, PA + PCG (identity smoother, %d-iter cap), "
@@ -435,7 +490,9 @@ def parse_args(argv=None):
     ap.add_argument("--nz", type=int, default=0, help="element layers in z (default n); a slab of the workload, e.g. one "
                     "rank's share of an 8-GPU run on one GPU (diagnostics, not a bench line)")
     ap.add_argument("--grains", type=int, default=0, help="grain count (default: BASELINE.json's for the mesh size)")
-    ap.add_argument("--krylov-iter", type=int, default=1000)
+    ap.add_argument("--config", type=int, default=4, choices=[4, 5], help="4: BASELINE.json configs[3], the headline FCC Voce / PA "
+                    "workload (default); 5: configs[4], HCP KMBalD + B-bar + EA + NRLS under cyclic loading")
+    ap.add_argument("--krylov-iter", type=int, default=0, help="PCG iteration cap (default: 1000, config 5: 2500 as in options_master.toml)")
     ap.add_argument("--true-jacobi", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-same-config", action="store_true", help="skip the sample-mesh GPU runs (N=1 only)")
@@ -447,6 +504,10 @@ def parse_args(argv=None):
     args = ap.parse_args(argv)
     if args.steps < 1 or args.warmup < 0 or args.gpus < 1:
         raise SystemExit("bench.py: need --steps >= 1, --warmup >= 0, --gpus >= 1")
+    if not args.krylov_iter:
+        args.krylov_iter = 2500 if args.config == 5 else 1000
+    if args.impl == "reference" and args.config != 4:
+        raise SystemExit("bench.py: the reference arm covers the headline configuration (--config 4) only")
     return args
 
 

@@ -355,11 +355,11 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
   c->cfg.e2n = nullptr;
   std::string msg = build_material(c->mat, cfg->xtal, cfg->slip, cfg->props, cfg->nprops);
   if (!msg.empty()) { delete c; return fail(msg); }
-  if (cfg->integ == EXAB200_INTEG_BBAR && cfg->assembly == EXAB200_PA) {
-    // mirrors the reference: B-bar has no PA gradient (src/mechanics_integrators.hpp:107-110)
-    delete c;
-    return fail("B-bar integration requires element assembly (EA)");
-  }
+  // integ_model = BBAR with assembly = PA is accepted like the reference accepts it: the residual and the diagonal are
+  // B-bar (ICExaNLFIntegrator::AssemblePA / AddMultPA / AssembleGradDiagonalPA, src/mechanics_integrators.cpp:1809-2088,
+  // 1607-1805) while the gradient apply is the plain operator, because ICExaNLFIntegrator inherits
+  // ExaNLFIntegrator::AssembleGradPA / AddMultGradPA (src/mechanics_integrators.hpp:107-110) -- a quirk of the reference
+  // (SURVEY.md App. C.4); production runs B-bar with EA.
   c->device = cfg->device;
   cudaError_t e = cudaSetDevice(c->device);
   if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaSetDevice"); }
@@ -638,6 +638,8 @@ int exab200_grad_diag_evec(exab200_ctx* c, double* d_diag_E, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (c->cfg.assembly == EXAB200_EA)
     k_ea_diag<EVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_E, io, c->cfg.nelems);
+  else if (c->cfg.integ == EXAB200_INTEG_BBAR)
+    k_grad_diag<EVEC, false, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_E, io, c->cfg.nelems, c->grad_dt);
   else
     k_grad_diag<EVEC><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_E, io, c->cfg.nelems, c->grad_dt);
   POST_LAUNCH(c);
@@ -652,6 +654,10 @@ int exab200_grad_diag(exab200_ctx* c, double* d_diag_L, void* stream) {
   ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
   if (c->cfg.assembly == EXAB200_EA)
     k_ea_diag<LVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_ea, d_diag_L, io, c->cfg.nelems);
+  else if (c->cfg.integ == EXAB200_INTEG_BBAR && c->tangent_fmt)
+    k_grad_diag<LVEC, true, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_tan, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
+  else if (c->cfg.integ == EXAB200_INTEG_BBAR)
+    k_grad_diag<LVEC, false, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_matgrad, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
   else if (c->tangent_fmt)
     k_grad_diag<LVEC, true><<<eblocks(c->cfg.nelems, 256), 256, 0, st>>>(c->d_tan, c->d_jac, d_diag_L, io, c->cfg.nelems, c->grad_dt);
   else

@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(256) k_residual(const double* __restrict__ str
 // lane = quadrature point; the 24 per-point partials are summed over the element with a
 // reduce-scatter butterfly (12 + 6 + 3 doubles), leaving node `lane`'s 3 entries in each lane.
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool COMPACT = false>
+template <int MODE, bool COMPACT = false, bool BBAR = false>
 __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ matgrad, const double* __restrict__ jac,
                                                    double* __restrict__ diag, ElemIO io, long nelems, double dt) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -708,8 +708,8 @@ __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ ma
   double v[8][3];
 #pragma unroll
   for (int a = 0; a < 8; ++a) v[a][0] = v[a][1] = v[a][2] = 0.0;
+  double J[9], adj[9], K[36], det = 1.0;
   if (active) {
-    double J[9], adj[9], K[36];
     const double* Jq = jac + (e * 8 + lane) * 9;
     const double* Kq = matgrad + (e * 8 + lane) * (COMPACT ? 32 : 36);
 #pragma unroll
@@ -723,7 +723,35 @@ __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ ma
 #pragma unroll
       for (int i = 0; i < 36; ++i) K[i] = Kq[i];
     }
-    const double det = adjugate(J, adj);
+    det = adjugate(J, adj);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) adj[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 36; ++i) K[i] = 0.0;
+  }
+  // B-bar (ICExaNLFIntegrator::AssembleGradDiagonalPA, src/mechanics_integrators.cpp:1607-1805): element-average shape
+  // gradients eDS(a,c) = sum_q W b_c(a,q) / sum_q W detJ (src/mechanics_integrators.cpp:1895-1952); lane a of the
+  // element's 8-lane group ends up holding node a's, every lane then fetches all eight by shuffle
+  double eds[8][3];
+  if (BBAR) {
+    const double w = active ? kWq : 0.0;
+    double vol = w * det;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) vol += shfl_xor_d(vol, m);
+    const double ivol = active ? 1.0 / vol : 0.0;
+    const double own0 = qp_grad_to_nodal(w * adj[0], w * adj[3], w * adj[6], lane) * ivol;
+    const double own1 = qp_grad_to_nodal(w * adj[1], w * adj[4], w * adj[7], lane) * ivol;
+    const double own2 = qp_grad_to_nodal(w * adj[2], w * adj[5], w * adj[8], lane) * ivol;
+    const int grp = (threadIdx.x & 31) & ~7;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      eds[a][0] = __shfl_sync(kFull, own0, grp | a);
+      eds[a][1] = __shfl_sync(kFull, own1, grp | a);
+      eds[a][2] = __shfl_sync(kFull, own2, grp | a);
+    }
+  }
+  if (active) {
     const double c = dt * kWq / det;
     const int vg[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
 #pragma unroll
@@ -732,17 +760,40 @@ __global__ void __launch_bounds__(256) k_grad_diag(const double* __restrict__ ma
       shape_grad(a, lane, g);
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) b[cc] = g[0] * adj[cc] + g[1] * adj[3 + cc] + g[2] * adj[6 + cc];
+      if (!BBAR) {
 #pragma unroll
-      for (int I = 0; I < 3; ++I) {
-        double s = 0.0;
+        for (int I = 0; I < 3; ++I) {
+          double s = 0.0;
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          double w = 0.0;
+          for (int p = 0; p < 3; ++p) {
+            double w = 0.0;
 #pragma unroll
-          for (int r = 0; r < 3; ++r) w += b[r] * K[vg[I][r] * 6 + vg[I][p]];
-          s += b[p] * w;
+            for (int r = 0; r < 3; ++r) w += b[r] * K[vg[I][r] * 6 + vg[I][p]];
+            s += b[p] * w;
+          }
+          v[a][I] = c * s;
         }
-        v[a][I] = c * s;
+      } else {
+        // columns of the 6x3 B-bar block of node a (rows in Voigt order), b normalised by detJ
+        const double idet = 1.0 / det, i3 = 1.0 / 3.0;
+        const double bx = b[0] * idet, by = b[1] * idet, bz = b[2] * idet;
+        const double b4 = i3 * (eds[a][0] - bx), b5 = b4 + bx;
+        const double b6 = i3 * (eds[a][1] - by), b7 = b6 + by;
+        const double b8 = i3 * (eds[a][2] - bz), b9 = b8 + bz;
+        const double Bb[3][6] = {{b5, b4, b4, 0.0, bz, by}, {b6, b7, b6, bz, 0.0, bx}, {b8, b8, b9, by, bx, 0.0}};
+        const double cw = dt * kWq * det;
+#pragma unroll
+        for (int I = 0; I < 3; ++I) {
+          double s = 0.0;
+#pragma unroll
+          for (int R = 0; R < 6; ++R) {
+            double w = 0.0;
+#pragma unroll
+            for (int S = 0; S < 6; ++S) w += K[S * 6 + R] * Bb[I][S];
+            s += Bb[I][R] * w;
+          }
+          v[a][I] = cw * s;
+        }
       }
     }
   }

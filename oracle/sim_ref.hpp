@@ -329,7 +329,9 @@ class VoxelSim {
 
   // Hform->GetGradient: AssembleGradPA / AssembleEA (+ diagonal)
   void get_gradient() {
-    if (cfg.assembly == 0 && cfg.integ == 0) {
+    // PA: the gradient is the plain operator also with B-bar integration (ICExaNLFIntegrator inherits
+    // ExaNLFIntegrator::AssembleGradPA / AddMultGradPA, src/mechanics_integrators.hpp:107-110)
+    if (cfg.assembly == 0) {
       c81.resize(ne * 8 * 81);
       D81.resize(ne * 8 * 81);
       transform_matgrad_4d(ne * 8, matgrad.data(), c81.data());
@@ -342,6 +344,7 @@ class VoxelSim {
     if (cfg.true_jacobi) {
       dvec dE(ne * 24, 0.0), d(ndof);
       if (cfg.assembly == 0 && cfg.integ == 0) assemble_grad_diag_pa(ne, dt, jac.data(), W.data(), G.data(), matgrad.data(), dE.data());
+      else if (cfg.assembly == 0) ic_assemble_grad_diag_pa(ne, dt, jac.data(), W.data(), G.data(), eds.data(), matgrad.data(), dE.data());
       else ea_diag(ne, ea.data(), dE.data());
       scatter(dE, d);
       for (long i = 0; i < ndof; ++i) dinv[i] = ess[i] ? 1.0 : 1.0 / d[i];
@@ -356,7 +359,7 @@ class VoxelSim {
         if (ess[i]) xm[i] = 0.0;
     dvec xE(ne * 24), yE(ne * 24, 0.0);
     gather(ne, nn, e2n.data(), xm.data(), xE.data());
-    if (cfg.assembly == 0 && cfg.integ == 0) addmult_grad_pa(ne, G.data(), D81.data(), xE.data(), yE.data());
+    if (cfg.assembly == 0) addmult_grad_pa(ne, G.data(), D81.data(), xE.data(), yE.data());
     else ea_mult(ne, ea.data(), xE.data(), yE.data());
     scatter(yE, y);
     if (!local_action)

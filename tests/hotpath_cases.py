@@ -88,9 +88,11 @@ def run_oracle_hot_path(case):
     xm = c["xvec"].copy()
     xm[ess] = 0.0
     xE = orc.gather(e2n, xm)
-    if c["assembly"] == 0 and c["integ"] == 0:
+    if c["assembly"] == 0:
+        # PA: plain gradient operator also with B-bar integration (the reference's ICExaNLFIntegrator inherits
+        # AssembleGradPA / AddMultGradPA); the diagonal is the B-bar one then (AssembleGradDiagonalPA override)
         yE = orc.grad_mult_pa(dt, jac, W, G, mg, xE)
-        dE = orc.grad_diag_pa(dt, jac, W, G, mg)
+        dE = orc.ic_grad_diag_pa(dt, jac, W, G, eds, mg) if c["integ"] == 1 else orc.grad_diag_pa(dt, jac, W, G, mg)
         out["y_grad_E_full"] = orc.grad_mult_pa(dt, jac, W, G, mg, orc.gather(e2n, c["xvec"]))
     else:
         ea = orc.ic_assemble_ea(dt, jac, W, G, eds, mg) if c["integ"] == 1 else orc.assemble_ea(dt, jac, W, G, mg)

@@ -38,3 +38,11 @@ def test_bench_runs_with_the_drivers_arguments():
 def test_bench_outlasting_the_dt_schedule():
     d = _run(["--steps", "2", "--warmup", "40", "--n", "8", "--no-cpu-baseline", "--no-same-config"])
     assert d["all_steps_converged"] and d["config"]["newton_iters"] >= 2
+
+
+def test_bench_config_5_line():
+    """BASELINE.json configs[4] as a second bench line: HCP KMBalD, B-bar + EA + NRLS, cyclic loading (small mesh here)"""
+    d = _run(["--config", "5", "--steps", "3", "--warmup", "10", "--n", "12", "--krylov-iter", "600"])
+    assert d["config"]["baseline_config"] == 5 and "HCP" in d["config"]["workload"] and d["all_steps_converged"]
+    assert d["roofline"]["kernel"].startswith("k_ea_mult_p") and d["roofline"]["achieved"] > 0
+    assert d["config"]["model_setups"] >= 3 * d["config"]["newton_iters"]      # line search: 3 residuals per iteration

@@ -90,7 +90,7 @@ def _operator_case(case):
 
 
 @pytest.mark.parametrize("n,assembly,integ", [(1, 0, 0), (2, 0, 0), (3, 0, 0), (5, 0, 0), (8, 0, 0), (1, 1, 1), (3, 1, 0), (4, 1, 1),
-                                              (5, 1, 1)])
+                                              (5, 1, 1), (1, 0, 1), (4, 0, 1)])
 def test_operator_kernels_match_oracle(n, assembly, integ):
     from oracle import orc
     case = hc.make_case(n=n, seed=20 + n, ngrains=4, assembly=assembly, integ=integ)
