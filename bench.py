@@ -173,6 +173,8 @@ def run_ours(args):
                         true_jacobi=args.true_jacobi, rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
     if nranks > 1 and not args.nccl_only:
         sim.enable_peer_collectives(dist)
+    if args.deterministic:
+        sim.set_deterministic(True)
     for tv in args.tuning:
         c, v = tv.split(":")
         sim.set_tuning(int(c), int(v))
@@ -247,7 +249,7 @@ def run_ours(args):
             "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%d^3 voxel, %d Voronoi grains, %s" % (n, ngrains, cfg["name"]), "baseline_config": args.config,
-                       "mesh": [n, n, nz], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi),
+                       "mesh": [n, n, nz], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi), "deterministic_scatter": bool(args.deterministic),
                        "cache": "inputs >> L2 (%.1f GB of quadrature data per rank)" % (ne_local * 8 * (36 + 9 + 2 * 28 + 12) * 8 / 1e9),
                        "newton_iters": newton, "pcg_iters": pcg, "model_setups": setups, "grad_mults": gmults},
             "e2e": {"value": newton / (e2e_ms * 1e-3), "unit": "Newton-steps/s",
@@ -494,6 +496,7 @@ def parse_args(argv=None):
                     "workload (default); 5: configs[4], HCP KMBalD + B-bar + EA + NRLS under cyclic loading")
     ap.add_argument("--krylov-iter", type=int, default=0, help="PCG iteration cap (default: 1000, config 5: 2500 as in options_master.toml)")
     ap.add_argument("--true-jacobi", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="owner-computes scatter: bitwise reproducible operator (A/B of its cost)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-same-config", action="store_true", help="skip the sample-mesh GPU runs (N=1 only)")
     ap.add_argument("--nccl-only", action="store_true", help="use NCCL for the CG-loop exchanges instead of the peer-memory kernels")

@@ -25,7 +25,7 @@ SYMBOLS = [
     "exab200_setup_jacobians", "exab200_model_setup", "exab200_model_setup_evec",
     "exab200_failed_points", "exab200_residual_evec", "exab200_residual", "exab200_grad_setup",
     "exab200_grad_mult_evec", "exab200_grad_mult", "exab200_grad_mult_ex", "exab200_grad_mult_halo_supported",
-    "exab200_grad_mult_halo", "exab200_grad_diag_evec", "exab200_grad_diag",
+    "exab200_grad_mult_halo", "exab200_set_deterministic", "exab200_grad_diag_evec", "exab200_grad_diag",
     "exab200_ea_assemble", "exab200_ea_mult_evec", "exab200_vol_sum", "exab200_calc_dp",
     "exab200_grad_calc", "exab200_launch_count", "exab200_set_tuning", "exab200_set_tangent_format",
 ]
@@ -180,6 +180,9 @@ class Context:
 
     def launch_count(self):
         return lib().exab200_launch_count(self._h)
+
+    def set_deterministic(self, on=True):
+        _chk(lib().exab200_set_deterministic(self._h, int(on)))
 
     def set_tangent_format(self, fmt):
         _chk(lib().exab200_set_tangent_format(self._h, int(fmt)))

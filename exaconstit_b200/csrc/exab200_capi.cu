@@ -60,10 +60,17 @@ struct exab200_ctx {
   unsigned long long* d_halo_cnt = nullptr;
   unsigned long long halo_tiles_cum = 0, halo_ctas_cum = 0;
   int halo_ctas = 16;  // exchange CTAs of the fused kernel (B200, 8 ranks: 8 -> 137 us, 16 -> 115 us per apply with 4-deep loads)
+  // deterministic (owner-computes) scatter: exab200_set_deterministic
+  int deterministic = 0;
+  int* d_n2e = nullptr;            // 8 slots per node: element*8 + native local node, ascending, -1 padded
+  double* d_yE = nullptr;          // E-vector scratch, 24 doubles per element
+  double* d_red_partial = nullptr; // block partials of the fixed-order reductions (gather dot, volume sums)
+  unsigned int* d_red_counter = nullptr;
   int variant_ea = 40, ctas_ea = 3;
   int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
+static constexpr int kRedBlocksMax = 1184;  // 8 x 148 SMs
 static inline unsigned eblocks(long nelems, int threads) { return (unsigned)((nelems * 8 + threads - 1) / threads); }
 #define NEED_L(c) \
   if (!(c) || !(c)->d_e2n) return fail("L-vector entry point needs e2n in the config")
@@ -168,6 +175,37 @@ static int launch_gmc(exab200_ctx* c, const double* x, double* y, ElemIO io, cud
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
   k_grad_mult_pa_c<NW, STAGES, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->tmap, x, y, io, c->cfg.nelems, c->grad_dt, dot,
                                                                            c->d_xend, HaloArgs{});
+  POST_LAUNCH(c);
+  return 0;
+}
+// owner-computes mode: the compact kernel writes the E-vector, k_evec_to_lvec sums per node in a fixed order
+template <bool ESS>
+static int launch_gmc_evout(exab200_ctx* c, const double* x, double* y, ElemIO io, cudaStream_t st, double* dot) {
+  constexpr int NW = 2, STAGES = 2;
+  constexpr int smem = NW * STAGES * kWarpStageBytesC + NW * STAGES * 8 + 1024;
+  static bool attr_set_dev[64] = {};
+  bool& attr_set = attr_set_dev[c->cfg.device & 63];
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_grad_mult_pa_c<NW, STAGES, ESS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long nwt = (c->cfg.nelems + 3) / 4;
+  long grid = (long)c->sm_count * c->ctas_c;
+  if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
+  k_grad_mult_pa_c<NW, STAGES, ESS, false, true><<<(unsigned)grid, NW * 32, smem, st>>>(c->tmap, x, c->d_yE, io, c->cfg.nelems,
+                                                                                        c->grad_dt, nullptr, c->d_xend, HaloArgs{});
+  POST_LAUNCH(c);
+  const unsigned gb = (unsigned)std::min<long>(std::min<long>((c->cfg.nnodes + 255) / 256, (long)c->sm_count * 8), kRedBlocksMax);
+  k_evec_to_lvec<ESS><<<gb, 256, 0, st>>>(c->d_yE, c->d_n2e, y, io.essmask, c->cfg.nnodes, 0, dot ? x : nullptr, c->d_red_partial,
+                                          c->d_red_counter, dot);
+  POST_LAUNCH(c);
+  return 0;
+}
+// E-vector scratch -> L-vector for the residual (essential dofs 0) and the diagonal (essential dofs 1)
+static int gather_evec(exab200_ctx* c, double* y, bool ess, int ess_one, cudaStream_t st) {
+  const unsigned gb = (unsigned)std::min<long>((c->cfg.nnodes + 255) / 256, (long)c->sm_count * 8);
+  if (ess) k_evec_to_lvec<true><<<gb, 256, 0, st>>>(c->d_yE, c->d_n2e, y, c->d_ess, c->cfg.nnodes, ess_one, nullptr, nullptr, nullptr, nullptr);
+  else k_evec_to_lvec<false><<<gb, 256, 0, st>>>(c->d_yE, c->d_n2e, y, nullptr, c->cfg.nnodes, ess_one, nullptr, nullptr, nullptr, nullptr);
   POST_LAUNCH(c);
   return 0;
 }
@@ -379,6 +417,10 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
   }
   CK(cudaMalloc(&c->d_fail, sizeof(int)));
   CK(cudaMemset(c->d_fail, 0, sizeof(int)));
+  // fixed-order reductions (volume sums, the deterministic gather's dot): block partials + arrival counters
+  CK(cudaMalloc(&c->d_red_partial, sizeof(double) * kRedBlocksMax * 41));
+  CK(cudaMalloc(&c->d_red_counter, 2 * sizeof(unsigned int)));
+  CK(cudaMemset(c->d_red_counter, 0, 2 * sizeof(unsigned int)));
   if (cfg->assembly == EXAB200_EA) CK(cudaMalloc(&c->d_ea, sizeof(double) * 576 * cfg->nelems));
   *out = c;
   return 0;
@@ -391,6 +433,7 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_ess);
   cudaFree(c->d_fail);
   cudaFree(c->d_halo_cnt);
+  cudaFree(c->d_n2e); cudaFree(c->d_yE); cudaFree(c->d_red_partial); cudaFree(c->d_red_counter);
   cudaFree(c->d_ea);
   cudaFree(c->d_xend);
   cudaFree(c->d_tan);
@@ -493,6 +536,16 @@ int exab200_residual_evec(exab200_ctx* c, const double* d_jac, const double* d_s
 
 int exab200_residual(exab200_ctx* c, const double* d_jac, const double* d_stress, double* d_y_L, void* stream) {
   NEED_L(c);
+  if (c->deterministic) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(c->d_yE, 0, sizeof(double) * 24 * c->cfg.nelems, st));
+    ElemIO ioe{nullptr, nullptr, 0};
+    const unsigned nbe = eblocks(c->cfg.nelems, 256);
+    if (c->cfg.integ == EXAB200_INTEG_BBAR) k_residual<EVEC, true><<<nbe, 256, 0, st>>>(d_stress, d_jac, c->d_yE, ioe, c->cfg.nelems);
+    else k_residual<EVEC, false><<<nbe, 256, 0, st>>>(d_stress, d_jac, c->d_yE, ioe, c->cfg.nelems);
+    POST_LAUNCH(c);
+    return gather_evec(c, d_y_L, c->have_ess, 0, st);
+  }
   CK(cudaMemsetAsync(d_y_L, 0, sizeof(double) * 3 * c->cfg.nnodes, (cudaStream_t)stream));
   ElemIO io{c->d_e2n, c->have_ess ? c->d_ess : nullptr, c->cfg.nnodes};
   const unsigned nb = eblocks(c->cfg.nelems, 256);
@@ -566,6 +619,10 @@ int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int
   if (c->tangent_fmt) {
     if (!(c->d_xend && c->xend_jac == c->d_jac))
       return fail("compact tangent records need the Jacobian array written by the last exab200_setup_jacobians call");
+    if (c->deterministic) {
+      if (ess) return launch_gmc_evout<true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+      return launch_gmc_evout<false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
+    }
     if (ess) return launch_grad_mult_compact<true>(c, d_x_L, d_y_L, io, st, d_dot_accum);
     return launch_grad_mult_compact<false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
   }
@@ -577,8 +634,32 @@ int exab200_grad_mult_ex(exab200_ctx* c, const double* d_x_L, double* d_y_L, int
   return launch_grad_mult_pa<LVEC, false>(c, d_x_L, d_y_L, io, st, d_dot_accum);
 }
 
+int exab200_set_deterministic(exab200_ctx* c, int on) {
+  NEED_L(c);
+  if (!on) { c->deterministic = 0; return 0; }
+  if (c->cfg.assembly != EXAB200_PA || !c->tangent_fmt)
+    return fail("the deterministic (owner-computes) scatter is implemented for the PA path with compact tangent records");
+  if (!c->d_n2e) {
+    const long ne = c->cfg.nelems, nn = c->cfg.nnodes;
+    std::vector<int> e2n(8 * ne), n2e(8 * nn, -1), fill(nn, 0);
+    CK(cudaMemcpy(e2n.data(), c->d_e2n, sizeof(int) * 8 * ne, cudaMemcpyDeviceToHost));
+    for (long e = 0; e < ne; ++e)
+      for (int a = 0; a < 8; ++a) {
+        const int nd = e2n[e * 8 + a];
+        if (fill[nd] >= 8) return fail("deterministic scatter: a node with more than 8 elements around it");
+        n2e[(long)nd * 8 + fill[nd]++] = (int)(e * 8 + a);
+      }
+    CK(cudaMalloc(&c->d_n2e, sizeof(int) * 8 * nn));
+    CK(cudaMemcpy(c->d_n2e, n2e.data(), sizeof(int) * 8 * nn, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_yE, sizeof(double) * 24 * ne));
+  }
+  c->deterministic = 1;
+  return 0;
+}
+
 int exab200_grad_mult_halo_supported(exab200_ctx* c, const exab200_halo* h) {
   if (!c || !h || !c->cfg.nnodes) return 0;
+  if (c->deterministic) return 0;                                           // owner-computes scatter: exchange separately
   if (c->cfg.assembly != EXAB200_PA || !c->tangent_fmt) return 0;          // compact-record PA kernel only
   if (h->nranks < 2 || h->nranks > 8 || h->layer_elems <= 0 || c->cfg.nelems % h->layer_elems) return 0;
   const long layers = c->cfg.nelems / h->layer_elems;
@@ -650,6 +731,15 @@ int exab200_grad_diag(exab200_ctx* c, double* d_diag_L, void* stream) {
   NEED_L(c);
   if (!c->d_matgrad) return fail("grad_setup has not been called");
   cudaStream_t st = (cudaStream_t)stream;
+  if (c->deterministic) {
+    CK(cudaMemsetAsync(c->d_yE, 0, sizeof(double) * 24 * c->cfg.nelems, st));
+    ElemIO ioe{nullptr, nullptr, 0};
+    const unsigned nbe = eblocks(c->cfg.nelems, 256);
+    if (c->cfg.integ == EXAB200_INTEG_BBAR) k_grad_diag<EVEC, true, true><<<nbe, 256, 0, st>>>(c->d_tan, c->d_jac, c->d_yE, ioe, c->cfg.nelems, c->grad_dt);
+    else k_grad_diag<EVEC, true, false><<<nbe, 256, 0, st>>>(c->d_tan, c->d_jac, c->d_yE, ioe, c->cfg.nelems, c->grad_dt);
+    POST_LAUNCH(c);
+    return gather_evec(c, d_diag_L, c->have_ess, 1, st);
+  }
   CK(cudaMemsetAsync(d_diag_L, 0, sizeof(double) * 3 * c->cfg.nnodes, st));
   ElemIO io{c->d_e2n, nullptr, c->cfg.nnodes};
   if (c->cfg.assembly == EXAB200_EA)
@@ -674,14 +764,14 @@ int exab200_vol_sum(exab200_ctx* c, const double* d_jac, const double* d_qf, int
   if (!c) return fail("null ctx");
   if (vdim < 1 || vdim > 40) return fail("vdim out of range (1..40)");
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(d_out, 0, sizeof(double) * (vdim + 1), st));
   const long npts = c->cfg.nelems * 8;
   long nb = (npts + 255) / 256;
   if (nb > (long)c->sm_count * 8) nb = (long)c->sm_count * 8;
+  if (nb > kRedBlocksMax) nb = kRedBlocksMax;
   if (vdim <= 9)
-    k_vol_sum<9><<<(unsigned)nb, 256, 0, st>>>(d_qf, d_jac, vdim, npts, d_out);
+    k_vol_sum<9><<<(unsigned)nb, 256, 0, st>>>(d_qf, d_jac, vdim, npts, d_out, c->d_red_partial, c->d_red_counter + 1);
   else
-    k_vol_sum<40><<<(unsigned)nb, 256, 0, st>>>(d_qf, d_jac, vdim, npts, d_out);
+    k_vol_sum<40><<<(unsigned)nb, 256, 0, st>>>(d_qf, d_jac, vdim, npts, d_out, c->d_red_partial, c->d_red_counter + 1);
   POST_LAUNCH(c);
   return 0;
 }

@@ -1568,6 +1568,8 @@ int exahost_kernel_time(exahost_sim* s, int which, double* total_ms, long* count
 }
 int exahost_set_tuning(exahost_sim* s, int ctas_per_sm, int variant) {
   // 95 / 96: reference 36-entry tangent layout / compact records (only meaningful before the first step)
+  // 97 / 98: deterministic (owner-computes) scatter on / off; the exchange then stays a separate kernel
+  if (variant == 97 || variant == 98) { s->comm.halo_fused = -1; return exab200_set_deterministic(s->ctx, variant == 97); }
   if (variant == 95 || variant == 96) return exab200_set_tangent_format(s->ctx, variant == 96 ? EXAB200_TANGENT_COMPACT : EXAB200_TANGENT_VOIGT36);
   return exab200_set_tuning(s->ctx, ctas_per_sm, variant);
 }

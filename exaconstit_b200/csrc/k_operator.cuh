@@ -415,7 +415,7 @@ struct HaloArgs {
 };
 
 // register cap: 12 resident warps per SM (6 CTAs of 2 warps, 3 of 4, 12 of 1)
-template <int NW, int STAGES, bool ESS, bool HALO = false>
+template <int NW, int STAGES, bool ESS, bool HALO = false, bool EVOUT = false>
 __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __grid_constant__ CUtensorMap tmap,
                                                             const double* __restrict__ x, double* __restrict__ y,
                                                             ElemIO io, long nelems, double dt,
@@ -575,10 +575,17 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
     const double y1 = qp_grad_to_nodal(t01, t11, t21, sg);
     const double y2 = qp_grad_to_nodal(t02, t12, t22, sg);
     if (active) {
-      xdoty += u0 * y0 + u1 * y1 + u2 * y2;
-      if (!(msk_c & 1)) red_add_f64(&y[nid_c], y0);
-      if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
-      if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], y2);
+      if (EVOUT) {
+        // owner-computes (deterministic) mode: the element's contributions go to an E-vector Y(a, i, e) with plain
+        // stores; k_evec_to_lvec sums them per node in a fixed order afterwards
+        const long o = ((tile_of(wt) << 2) + el) * 24 + lex_to_native(lane);
+        y[o] = y0; y[o + 8] = y1; y[o + 16] = y2;
+      } else {
+        xdoty += u0 * y0 + u1 * y1 + u2 * y2;
+        if (!(msk_c & 1)) red_add_f64(&y[nid_c], y0);
+        if (!(msk_c & 2)) red_add_f64(&y[io.nnodes + nid_c], y1);
+        if (!(msk_c & 4)) red_add_f64(&y[2 * io.nnodes + nid_c], y2);
+      }
     }
     if (HALO && wt < nb) {  // a boundary-layer tile is complete: count it off for the exchange CTAs
       __threadfence();
@@ -1208,7 +1215,8 @@ __global__ void __launch_bounds__(256) k_ea_diag(const double* __restrict__ ea, 
 // ------------------------------------------------------------------------------------------
 template <int VDIM_MAX>
 __global__ void __launch_bounds__(256) k_vol_sum(const double* __restrict__ qf, const double* __restrict__ jac, int vdim,
-                                                 long npts, double* __restrict__ out) {
+                                                 long npts, double* __restrict__ out, double* __restrict__ partial,
+                                                 unsigned int* __restrict__ counter) {
   __shared__ double red[8][VDIM_MAX + 1];
   double acc[VDIM_MAX + 1];
 #pragma unroll
@@ -1233,13 +1241,84 @@ __global__ void __launch_bounds__(256) k_vol_sum(const double* __restrict__ qf, 
 #pragma unroll
     for (int c = 0; c <= VDIM_MAX; ++c) red[warp][c] = acc[c];
   __syncthreads();
+  // block partials, then the last block to finish sums them in block order: bitwise reproducible averages
+  __shared__ bool last;
   if (threadIdx.x <= VDIM_MAX) {
     const int c = threadIdx.x;
     double s = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][c];
-    if (c < vdim) red_add_f64(&out[c], s);
-    else if (c == VDIM_MAX) red_add_f64(&out[vdim], s);
+    partial[(long)blockIdx.x * (VDIM_MAX + 1) + c] = s;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x <= VDIM_MAX) {
+    const int c = threadIdx.x;
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partial[(long)b * (VDIM_MAX + 1) + c]);
+    if (c < vdim) out[c] = s;
+    else if (c == VDIM_MAX) out[vdim] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Owner-computes scatter (the deterministic operator option): y_L(node) = sum of the E-vector entries of the elements
+// around the node, in ascending element order (n2e: 8 slots per node, element*8 + native local node, -1 padded) -- the
+// role of ElementRestriction::MultTranspose (src/mechanics_operator_ext.cpp:149) without atomics, so the operator, the
+// residual and the diagonal are bitwise reproducible run to run.  With x != nullptr the block partial sums of
+// x_masked . y are written too and the last block adds them in block order into *dot_out (the CG denominator).
+// ------------------------------------------------------------------------------------------
+template <bool ESS>
+__global__ void __launch_bounds__(256) k_evec_to_lvec(const double* __restrict__ yE, const int* __restrict__ n2e,
+                                                      double* __restrict__ yL, const unsigned char* __restrict__ essmask,
+                                                      long nnodes, int ess_value_is_one, const double* __restrict__ x,
+                                                      double* __restrict__ partial, unsigned int* __restrict__ counter,
+                                                      double* __restrict__ dot_out) {
+  double dot = 0.0;
+  for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nnodes; n += (long)gridDim.x * blockDim.x) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const int4 s0 = reinterpret_cast<const int4*>(n2e)[2 * n], s1 = reinterpret_cast<const int4*>(n2e)[2 * n + 1];
+    const int ids[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (ids[k] >= 0) {
+        const long o = (long)(ids[k] >> 3) * 24 + (ids[k] & 7);
+        a0 += yE[o]; a1 += yE[o + 8]; a2 += yE[o + 16];
+      }
+    }
+    const unsigned msk = ESS ? essmask[n] : 0u;
+    const double fill = ess_value_is_one ? 1.0 : 0.0;
+    if (x) {
+      if (!(msk & 1)) dot += x[n] * a0;
+      if (!(msk & 2)) dot += x[nnodes + n] * a1;
+      if (!(msk & 4)) dot += x[2 * nnodes + n] * a2;
+    }
+    yL[n] = (msk & 1) ? fill : a0;
+    yL[nnodes + n] = (msk & 2) ? fill : a1;
+    yL[2 * nnodes + n] = (msk & 4) ? fill : a2;
+  }
+  if (!x) return;
+  __shared__ double red[8];
+  __shared__ bool last;
+  for (int m = 16; m > 0; m >>= 1) dot += __shfl_xor_sync(kFull, dot, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    __threadfence();
+    last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
+  double t = 0.0;
+  for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&partial[b]);
+  *dot_out += t;
 }
 
 }  // namespace exab

@@ -195,6 +195,10 @@ class VoxelSim:
         lib().exahost_kernel_time(self._h, {"grad_mult": 0, "model_setup": 1}[which], C.byref(tot), C.byref(cnt), int(reset))
         return tot.value, cnt.value
 
+    def set_deterministic(self, on=True):
+        """Owner-computes scatter (exab200_set_deterministic): bitwise reproducible operator, residual and diagonal."""
+        _chk(lib().exahost_set_tuning(self._h, 1, 97 if on else 98))
+
     def set_tuning(self, ctas_per_sm, variant):
         _chk(lib().exahost_set_tuning(self._h, ctas_per_sm, variant))
 

@@ -145,6 +145,14 @@ int exab200_grad_mult_halo_supported(exab200_ctx* ctx, const exab200_halo* h);
 int exab200_grad_mult_halo(exab200_ctx* ctx, const double* d_x_L, double* d_y_L, int flags, double* d_dot_accum,
                            const exab200_halo* h, void* stream);
 
+/* Deterministic operator option.  By default the L-vector kernels scatter element contributions with
+ * red.global.add.f64, whose order varies run to run (results differ in the last bits).  With on != 0 the gradient
+ * apply, the residual and the diagonal write E-vectors and a second kernel sums the contributions of the (at most 8)
+ * elements around every node in ascending element order -- the explicit form of ElementRestriction::MultTranspose
+ * (src/mechanics_operator_ext.cpp:149,198) -- and x^T K x is reduced in a fixed order: bitwise reproducible results at
+ * the cost of one extra E-vector round trip per apply.  PA with compact tangent records only. */
+int exab200_set_deterministic(exab200_ctx* ctx, int on);
+
 /* AssembleGradDiagonalPA / EA AssembleDiagonal (src/mechanics_integrators.cpp:625-748,1607-1805;
  * src/mechanics_operator_ext.cpp:95-123,228-265).  L form: diag[ess] = 1. */
 int exab200_grad_diag_evec(exab200_ctx* ctx, double* d_diag_E, void* stream);

@@ -266,3 +266,49 @@ def test_compact_tangent_path(n, xtal, kin, variant, ctas):
     for k in ("y", "d", "y2", "yl"):
         assert hc.rel_err(b[k], a[k]) < 1e-12, k
     assert abs(a["acc"] - b["acc"]) / abs(a["acc"]) < 1e-12
+
+
+@pytest.mark.parametrize("n,integ", [(1, 0), (6, 0), (9, 0), (5, 1)])
+def test_deterministic_scatter_option(n, integ):
+    """exab200_set_deterministic: gradient apply (+ fused x^T K x), residual and diagonal through the owner-computes
+    gather equal the atomic-scatter path to round-off and are bitwise identical from call to call."""
+    import torch
+    from exaconstit_b200 import capi
+    case = hc.make_case(n=n, seed=80 + n, ngrains=4, integ=integ)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    T = lambda a: torch.tensor(np.ascontiguousarray(a), **f64)
+    ne, nn, nsv, dt = case["ne"], case["nn"], case["nsv"], case["dt"]
+    ctx = capi.Context(0, 0, case["props"], 298.0, ne, nn, case["e2n"], 0, integ)
+    with pytest.raises(capi.Exab200Error):
+        ctx.set_deterministic(True)                     # needs the compact tangent records
+    ctx.set_essential_mask(case["essmask"])
+    ctx.set_tangent_format(1)
+    jac = torch.empty(ne * 72, **f64)
+    ctx.setup_jacobians(T(case["xbeg"]), T(case["vel"]), dt, jac)
+    s1, h1, mg = torch.empty(ne * 48, **f64), torch.empty(ne * 8 * nsv, **f64), torch.zeros(ne * 8 * 36, **f64)
+    ctx.model_setup(dt, jac, T(case["vel"]), T(case["stress0"]), T(case["hist0"]), s1, h1, mg)
+    ctx.grad_setup(dt, mg, jac)
+    x = T(case["xvec"])
+
+    def run():
+        y, yl, d, r = (torch.empty(3 * nn, **f64) for _ in range(4))
+        acc = torch.zeros(1, **f64)
+        ctx.grad_mult_ex(x, y, flags=0, dot_accum=acc)
+        ctx.grad_mult(x, yl, local_action=True)
+        ctx.grad_diag(d)
+        ctx.residual(jac, s1, r)
+        torch.cuda.synchronize()
+        return [t.cpu().numpy() for t in (y, yl, d, r)] + [acc.item()]
+
+    ref = run()
+    ctx.set_deterministic(True)
+    a, b = run(), run()
+    for u, v, w in zip(a[:4], b[:4], ref[:4]):
+        assert np.array_equal(u, v)
+        assert hc.rel_err(u, w) < 1e-13
+    assert a[4] == b[4] and abs(a[4] - ref[4]) <= 1e-12 * abs(ref[4])
+    ctx.set_deterministic(False)
+    c = run()
+    for u, w in zip(c[:4], ref[:4]):
+        assert hc.rel_err(u, w) < 1e-13
+    ctx.close()
