@@ -426,10 +426,10 @@ __global__ void __launch_bounds__(256) k_cg_step1_fused(double* __restrict__ x, 
   }
 }
 
-// The whole vector part of a CG iteration in ONE launch: step 1 (x += alpha d, r -= alpha z, betanom = r.Mr with the
+// The whole vector part of a CG iteration in ONE launch: step 1 (r -= alpha z, betanom = r.Mr with the
 // block reduction, the fixed-order final sum and -- for nranks > 1 -- the peer-memory all-reduce done by the last
-// block to arrive), a grid-wide barrier on a generation flag, then step 2 (d = M r + beta d, z = 0) on the same
-// slices while r is still in L2.  Replaces k_cg_step1_fused + k_cg_step2 (one launch and one full re-read of r and d
+// block to arrive; z = 0 for the next apply), a grid-wide barrier on a generation flag, then x += alpha d and step 2
+// (d = M r + beta d) on the same slices while r is still in L2: nine vector passes instead of ten.  Replaces k_cg_step1_fused + k_cg_step2 (one launch and one full re-read of r and d
 // less per iteration).  All blocks must be co-resident (the grid is sized from the occupancy query by the caller).
 __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double* __restrict__ r, double* __restrict__ d,
                                                   double* __restrict__ z, const double* __restrict__ dinv,
@@ -447,7 +447,6 @@ __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double
     const long off = c * nn;
     for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
       const long i = off + n;
-      x[i] += alpha * d[i];
       const double rn = r[i] - alpha * z[i];
       r[i] = rn;
       z[i] = 0.0;  // output of the next operator apply
@@ -509,8 +508,9 @@ __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double
     const long off = c * nn;
     for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
       const long i = off + n;
-      const double ri = r[i];
-      d[i] = (dinv ? dinv[i] * ri : ri) + beta * d[i];
+      const double ri = r[i], di = d[i];
+      x[i] += alpha * di;   // step 1's solution update, done here where d is read anyway (one vector pass less)
+      d[i] = (dinv ? dinv[i] * ri : ri) + beta * di;
     }
   }
 }

@@ -87,6 +87,18 @@ int run(const std::string& opt_file, bool check_only) {
   // ---- text inputs ----
   const std::vector<double> props = load_numbers(o.props_file, o.nProps, "material properties");
   (void)load_numbers(o.state_file, o.numStateVars, "state variables");  // values are re-initialised by the model (init_state_vars)
+  // Parity notice ('Oracle and parity status'): ExaCMech's source is not part of the reference tree; the
+  // restated KMBalD kinetics are pinned by the reference's goldens only for p = q = 1, and nothing pins HCP.
+  if (o.slip_type == SlipType::MTSDD) {
+    const bool hcp = o.xtal_type == XtalType::HCP;
+    // p, q follow mu_ref, T_ref, c_1 (x4 slip families for HCP), tau_a in the property vector (scripts/ecmech_prop_file.py)
+    const size_t ip = (hcp ? 8 : 6) + 2 + (hcp ? 4 : 1) + 1;
+    if (hcp)
+      std::printf("warning: HCP crystals have no reference property set or golden output; results are NOT pinned to the reference\n");
+    else if (props.size() > ip + 1 && (props[ip] != 1.0 || props[ip + 1] != 1.0))
+      std::printf("warning: KMBalD kinetics with p = %g, q = %g: the reference's mtsdd_full_auto golden is NOT reproduced in this "
+                  "regime (6 %% at 1 %% strain); results are not pinned to the reference\n", props[ip], props[ip + 1]);
+  }
   if (o.ngrains < 1) throw Abort("Properties.Grain.num_grains must be positive for a crystal-plasticity run");
   const std::vector<double> quats = load_numbers(o.ori_file, 4L * o.ngrains, "orientation");
   const long ne_coarse = (long)o.nxyz[0] * o.nxyz[1] * o.nxyz[2];
