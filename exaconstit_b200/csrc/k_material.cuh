@@ -57,7 +57,14 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant
   nodal_to_qp_grad(v0, lane, d[0][0], d[0][1], d[0][2]);
   nodal_to_qp_grad(v1, lane, d[1][0], d[1][1], d[1][2]);
   nodal_to_qp_grad(v2, lane, d[2][0], d[2][1], d[2][2]);
+#ifdef EXAB_K1_LOCKSTEP
+  if (!active) {  // keep the barrier count of the CTA-lockstep solve loop
+    while (__syncthreads_or(0)) {}
+    return;
+  }
+#else
   if (!active) return;
+#endif
   const long p = e * 8 + lane;
   double L[3][3];
   {

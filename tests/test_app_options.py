@@ -42,6 +42,10 @@ def test_changing_mixed_bcs_and_auto_time(tmp_path):
     assert r.returncode == 0, r.stderr
     assert "nsteps 200 auto 1 cust 0 dt 0.1 dt_min 0.05 dt_scale 0.333333 t_final 10" in r.stdout
     assert "running the matrix-free PA operator" in r.stdout
+    # parity notice: this regime of the KMBalD kinetics is not pinned to the reference
+    assert "warning: KMBalD kinetics with p = 0.8, q = 1.4" in r.stdout and "not pinned to the reference" in r.stdout
+    r = _check(tmp_path, xtal="bcc", slip="mtsdd", props_key="props_cp_mts")
+    assert r.returncode == 0 and "warning" not in r.stdout          # p = q = 1: pinned by mtsdd_bcc / mtsdd_full
 
 
 @pytest.mark.parametrize("kw,msg", [

@@ -16,7 +16,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rows of `ncu --page raw --csv`: from an .ncu-rep, or from a .csv exported on the GPU box (the reports of a
+    --set full capture are too large to bring back through gpurun_out/)"""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
@@ -38,7 +43,13 @@ def main(rep):
                     pass
         for v, k in sorted(st, reverse=True)[:8]:
             print("    %-28s %.3f" % (k, v))
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        import gzip
+        import os
+        sp = rep.replace(".raw.csv", ".source.csv.gz")
+        src = gzip.open(sp, "rt").read() if os.path.exists(sp) else ""
+    else:
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     hi = next((i for i, r in enumerate(rows) if "# Samples" in r), None)
     if hi is not None:
