@@ -171,8 +171,9 @@ def run_ours(args):
     sim = host.VoxelSim((n, n, nz), (1.0, 1.0, nz / n), cfg["xtal"], cfg["kin"], cfg["props"], 298.0, grains, quats,
                         assembly=cfg["assembly"], integ=cfg["integ"], nl_solver=cfg["nl_solver"], nr=cfg["nr"], kr=cfg["kr"],
                         true_jacobi=args.true_jacobi, rank=rank, nranks=nranks, device=local, nccl_id=nccl_id)
+    p2p = False
     if nranks > 1 and not args.nccl_only:
-        sim.enable_peer_collectives(dist)
+        p2p = sim.enable_peer_collectives(dist)      # False: a peer mailbox could not be mapped -> NCCL exchanges on all ranks
     if args.deterministic:
         sim.set_deterministic(True)
     for tv in args.tuning:
@@ -249,7 +250,7 @@ def run_ours(args):
             "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%d^3 voxel, %d Voronoi grains, %s" % (n, ngrains, cfg["name"]), "baseline_config": args.config,
-                       "mesh": [n, n, nz], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory kernels" if (nranks > 1 and not args.nccl_only) else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi), "deterministic_scatter": bool(args.deterministic),
+                       "mesh": [n, n, nz], "partition": "z-slab x%d" % nranks, "collectives": ("nvlink peer-memory (exchange and all-reduces inside the operator / CG kernels)" if p2p else ("nccl" if nranks > 1 else "none")), "true_jacobi": bool(args.true_jacobi), "deterministic_scatter": bool(args.deterministic),
                        "cache": "inputs >> L2 (%.1f GB of quadrature data per rank)" % (ne_local * 8 * (36 + 9 + 2 * 28 + 12) * 8 / 1e9),
                        "newton_iters": newton, "pcg_iters": pcg, "model_setups": setups, "grad_mults": gmults},
             "e2e": {"value": newton / (e2e_ms * 1e-3), "unit": "Newton-steps/s",

@@ -67,7 +67,10 @@ struct exab200_ctx {
   double* d_red_partial = nullptr; // block partials of the fixed-order reductions (gather dot, volume sums)
   unsigned int* d_red_counter = nullptr;
   int variant_ea = 40, ctas_ea = 3;
-  int k1_min_blocks = 2;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
+#ifndef EXAB_K1_MINB_DEFAULT
+#define EXAB_K1_MINB_DEFAULT 2
+#endif
+  int k1_min_blocks = EXAB_K1_MINB_DEFAULT;  // K1 occupancy target (blocks of 128 threads per SM)  // PA gradient-apply tile configuration, see kVariants
 };
 
 static constexpr int kRedBlocksMax = 1184;  // 8 x 148 SMs
@@ -351,6 +354,7 @@ template <int NSLIP, int KIN, int MODE>
 static int launch_k1_occ(exab200_ctx* c, double dt, const double* d_jac, const double* d_vel, const double* s0,
                          const double* h0, double* s1, double* h1, double* mg, cudaStream_t st) {
   switch (c->k1_min_blocks) {
+    case 1: return launch_k1<NSLIP, KIN, MODE, 1>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
     case 2: return launch_k1<NSLIP, KIN, MODE, 2>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
     default: return launch_k1<NSLIP, KIN, MODE, 3>(c, dt, d_jac, d_vel, s0, h0, s1, h1, mg, st);
   }

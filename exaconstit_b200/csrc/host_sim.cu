@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) k_cg_step1_fused(double* __restrict__ x, 
 // block to arrive; z = 0 for the next apply), a grid-wide barrier on a generation flag, then x += alpha d and step 2
 // (d = M r + beta d) on the same slices while r is still in L2: nine vector passes instead of ten.  Replaces k_cg_step1_fused + k_cg_step2 (one launch and one full re-read of r and d
 // less per iteration).  All blocks must be co-resident (the grid is sized from the occupancy query by the caller).
-__global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double* __restrict__ r, double* __restrict__ d,
+__global__ void __launch_bounds__(256, 4) k_cg_fused(double* __restrict__ x, double* __restrict__ r, double* __restrict__ d,
                                                   double* __restrict__ z, const double* __restrict__ dinv,
                                                   const double* __restrict__ nom, const double* __restrict__ den, long nn,
                                                   long n_owned, double* __restrict__ partial, double* __restrict__ den_next,
@@ -443,14 +443,28 @@ __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double
   const double alpha = nom_v / *den;
   if (blockIdx.x == 0 && threadIdx.x == 0) *den_next = 0.0;  // accumulator of the next fused d^T A d
   double s = 0.0;
+  // four independent elements per thread and pass: with one, the loads in flight (151 k threads x 2 x 8 B) cover only
+  // half of what HBM needs (ncu: 50 % DRAM throughput, long_scoreboard 69 per issue)
+  const long first = (long)blockIdx.x * blockDim.x + threadIdx.x, step = (long)gridDim.x * blockDim.x;
   for (int c = 0; c < 3; ++c) {
     const long off = c * nn;
-    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
-      const long i = off + n;
-      const double rn = r[i] - alpha * z[i];
-      r[i] = rn;
-      z[i] = 0.0;  // output of the next operator apply
-      if (n < n_owned) s += rn * (dinv ? dinv[i] * rn : rn);
+    for (long n = first; n < nn; n += 4 * step) {
+      double rv[4], zv[4], mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long m = n + u * step;
+        if (m < nn) { rv[u] = r[off + m]; zv[u] = z[off + m]; mv[u] = dinv ? dinv[off + m] : 1.0; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long m = n + u * step;
+        if (m < nn) {
+          const double rn = rv[u] - alpha * zv[u];
+          r[off + m] = rn;
+          z[off + m] = 0.0;  // output of the next operator apply
+          if (m < n_owned) s += rn * (dinv ? mv[u] * rn : rn);
+        }
+      }
     }
   }
   __shared__ double red[8];
@@ -506,11 +520,21 @@ __global__ void __launch_bounds__(256) k_cg_fused(double* __restrict__ x, double
   const double beta = ld_cg(d_bet) / nom_v;
   for (int c = 0; c < 3; ++c) {
     const long off = c * nn;
-    for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < nn; n += (long)gridDim.x * blockDim.x) {
-      const long i = off + n;
-      const double ri = r[i], di = d[i];
-      x[i] += alpha * di;   // step 1's solution update, done here where d is read anyway (one vector pass less)
-      d[i] = (dinv ? dinv[i] * ri : ri) + beta * di;
+    for (long n = first; n < nn; n += 4 * step) {
+      double rv[4], dv[4], xv[4], mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long m = n + u * step;
+        if (m < nn) { rv[u] = r[off + m]; dv[u] = d[off + m]; xv[u] = x[off + m]; mv[u] = dinv ? dinv[off + m] : 1.0; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long m = n + u * step;
+        if (m < nn) {
+          x[off + m] = xv[u] + alpha * dv[u];   // step 1's solution update, done here where d is read anyway
+          d[off + m] = (dinv ? mv[u] * rv[u] : rv[u]) + beta * dv[u];
+        }
+      }
     }
   }
 }
@@ -564,6 +588,11 @@ class SlabComm {
     std::memcpy(out64, &h, 64);
   }
   void SetPeers(const void* handles) {
+    if (!handles) {  // back to the NCCL exchanges (a rank could not map a peer's mailbox)
+      use_p2p = false;
+      halo_fused = -1;
+      return;
+    }
     for (int r = 0; r < nranks; ++r) {
       if (r == rank) { peers.p[r] = mailbox.d; continue; }
       cudaIpcMemHandle_t h;

@@ -27,7 +27,10 @@ namespace exab {
 // (conflict-free, and off the local-memory / L2 path).
 // fail_count is incremented for points whose local solve did not converge.
 // ------------------------------------------------------------------------------------------
-constexpr int kJS = 128;
+#ifndef EXAB_K1_THREADS
+#define EXAB_K1_THREADS 128
+#endif
+constexpr int kJS = EXAB_K1_THREADS;
 constexpr int kK1SmemBytes = 64 * kJS * 8;  // 64 KB: one 8x8 Jacobian per thread
 template <int NSLIP, int KIN, int MODE, int MINB>
 __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant__ MatDev m, double dt,

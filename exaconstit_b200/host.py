@@ -177,15 +177,26 @@ class VoxelSim:
         handles of the ranks' mailboxes over `dist` (torch.distributed) and map them."""
         import torch
         if self.nranks == 1:
-            return
+            return False
         buf = (C.c_char * 64)()
         _chk(lib().exahost_comm_handle(self._h, buf))
         mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda")
         allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(self.nranks)]
         dist.all_gather(allh, mine)
         blob = b"".join(bytes(t.cpu().tolist()) for t in allh)
-        _chk(lib().exahost_set_peers(self._h, C.create_string_buffer(blob, len(blob))))
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            _chk(lib().exahost_set_peers(self._h, C.create_string_buffer(blob, len(blob))))
+        except HostError as e:   # no peer access to a neighbour (topology / IPC restrictions)
+            ok.zero_()
+            self.peer_error = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # all ranks or none: the protocols must match
+        if int(ok.item()) == 0:
+            _chk(lib().exahost_set_peers(self._h, None))
+            dist.barrier()
+            return False
         dist.barrier()
+        return True
 
     def kernel_timing(self, enable=True):
         lib().exahost_kernel_timing(self._h, int(enable))
