@@ -36,6 +36,7 @@ struct exab200_ctx {
   unsigned char* d_ess = nullptr;
   bool have_ess = false;
   int* d_fail = nullptr;
+  double* d_k1_idle = nullptr;  // scratch records for the idle threads of K1's last CTA
   // gradient operator state
   double grad_dt = 0.0;
   const double* d_matgrad = nullptr;
@@ -346,7 +347,7 @@ static int launch_k1(exab200_ctx* c, double dt, const double* d_jac, const doubl
   k_model_setup<NSLIP, KIN, MODE, MINB><<<nb, kJS, kK1SmemBytes, st>>>(c->mat, dt, d_jac, d_vel,
                                                                          MODE == LVEC ? c->d_e2n : nullptr, c->cfg.nnodes, s0, h0, s1,
                                                                          h1, c->tangent_fmt ? c->d_tan : mg, c->cfg.nelems,
-                                                                         c->tangent_fmt ? mat::kTangentCompact : 1, c->d_fail);
+                                                                         c->tangent_fmt ? mat::kTangentCompact : 1, c->d_fail, c->d_k1_idle);
   POST_LAUNCH(c);
   return 0;
 }
@@ -421,6 +422,7 @@ int exab200_create(const exab200_config* cfg, exab200_ctx** out) {
   }
   CK(cudaMalloc(&c->d_fail, sizeof(int)));
   CK(cudaMemset(c->d_fail, 0, sizeof(int)));
+  CK(cudaMalloc(&c->d_k1_idle, sizeof(double) * kJS * kIdleRecord));
   // fixed-order reductions (volume sums, the deterministic gather's dot): block partials + arrival counters
   CK(cudaMalloc(&c->d_red_partial, sizeof(double) * kRedBlocksMax * 41));
   CK(cudaMalloc(&c->d_red_counter, 2 * sizeof(unsigned int)));
@@ -436,6 +438,7 @@ void exab200_destroy(exab200_ctx* c) {
   cudaFree(c->d_e2n);
   cudaFree(c->d_ess);
   cudaFree(c->d_fail);
+  cudaFree(c->d_k1_idle);
   cudaFree(c->d_halo_cnt);
   cudaFree(c->d_n2e); cudaFree(c->d_yE); cudaFree(c->d_red_partial); cudaFree(c->d_red_counter);
   cudaFree(c->d_ea);

@@ -32,6 +32,7 @@ namespace exab {
 #endif
 constexpr int kJS = EXAB_K1_THREADS;
 constexpr int kK1SmemBytes = 64 * kJS * 8;  // 64 KB: one 8x8 Jacobian per thread
+constexpr int kIdleRecord = 96;            // doubles per idle thread: history (<= 40) | stress (6) | tangent (36)
 template <int NSLIP, int KIN, int MODE, int MINB>
 __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant__ MatDev m, double dt,
                                                            const double* __restrict__ jac,
@@ -39,7 +40,8 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant
                                                            long nnodes, const double* __restrict__ stress0,
                                                            const double* __restrict__ hist0, double* __restrict__ stress1,
                                                            double* __restrict__ hist1, double* __restrict__ matgrad,
-                                                           long nelems, int layout, int* __restrict__ fail_count) {
+                                                           long nelems, int layout, int* __restrict__ fail_count,
+                                                           double* __restrict__ idle_scratch) {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 7;
   const long e = gt >> 3;
@@ -61,14 +63,14 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant
   nodal_to_qp_grad(v1, lane, d[1][0], d[1][1], d[1][2]);
   nodal_to_qp_grad(v2, lane, d[2][0], d[2][1], d[2][2]);
 #ifdef EXAB_K1_LOCKSTEP
-  if (!active) {  // keep the barrier count of the CTA-lockstep solve loop
-    while (__syncthreads_or(0)) {}
-    return;
-  }
+  // CTA-lockstep solve loop: every thread of the CTA has to run it (a barrier per pass).  The inactive threads of the
+  // last CTA shadow point 0 with a zero velocity gradient (d = 0 from the butterfly of zeros: a one-pass solve) and
+  // write into a scratch record instead of the output arrays.
+  const long p = active ? e * 8 + lane : 0;
 #else
   if (!active) return;
-#endif
   const long p = e * 8 + lane;
+#endif
   double L[3][3];
   {
     double J[9], adj[9];
@@ -81,9 +83,18 @@ __global__ void __launch_bounds__(kJS, MINB) k_model_setup(const __grid_constant
       for (int t = 0; t < 3; ++t) L[i][t] = (d[i][0] * adj[t] + d[i][1] * adj[3 + t] + d[i][2] * adj[6 + t]) * idet;
   }
   extern __shared__ double smJ[];
-  const int nf = mat::update_point<NSLIP, KIN, kJS>(m, dt, L, hist0 + p * nsv, stress0 + p * 6, hist1 + p * nsv,
-                                                    stress1 + p * 6, matgrad + p * (layout == mat::kTangentCompact ? 32 : 36), layout, smJ + threadIdx.x);
-  if (nf < 0) atomicAdd(fail_count, 1);
+  double* h1p = hist1 + p * nsv;
+  double* s1p = stress1 + p * 6;
+  double* kp = matgrad + p * (layout == mat::kTangentCompact ? 32 : 36);
+#ifdef EXAB_K1_LOCKSTEP
+  if (!active) {
+    double* rec = idle_scratch + (long)threadIdx.x * kIdleRecord;
+    h1p = rec; s1p = rec + 48; kp = rec + 56;
+  }
+#endif
+  const int nf = mat::update_point<NSLIP, KIN, kJS>(m, dt, L, hist0 + p * nsv, stress0 + p * 6, h1p, s1p, kp, layout,
+                                                    smJ + threadIdx.x);
+  if (nf < 0 && active) atomicAdd(fail_count, 1);
 }
 
 // init_state_vars (src/mechanics_ecmech.hpp:249-300): overwrite the ExaCMech-owned history slots
