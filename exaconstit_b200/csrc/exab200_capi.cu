@@ -34,6 +34,7 @@ struct exab200_ctx {
   int device = 0, sm_count = 148;
   int* d_e2n = nullptr;
   unsigned char* d_ess = nullptr;
+  int* d_e2n_ess = nullptr;     // connectivity with the essential-dof bits in bits 28..30 (compact PA apply)
   bool have_ess = false;
   int* d_fail = nullptr;
   double* d_k1_idle = nullptr;  // scratch records for the idle threads of K1's last CTA
@@ -177,6 +178,7 @@ static int launch_gmc(exab200_ctx* c, const double* x, double* y, ElemIO io, cud
   const long nwt = (c->cfg.nelems + 3) / 4;
   long grid = (long)c->sm_count * c->ctas_c;
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
+  if (ESS) io.e2n = c->d_e2n_ess;
   k_grad_mult_pa_c<NW, STAGES, ESS><<<(unsigned)grid, NW * 32, smem, st>>>(c->tmap, x, y, io, c->cfg.nelems, c->grad_dt, dot,
                                                                            c->d_xend, HaloArgs{});
   POST_LAUNCH(c);
@@ -196,6 +198,7 @@ static int launch_gmc_evout(exab200_ctx* c, const double* x, double* y, ElemIO i
   const long nwt = (c->cfg.nelems + 3) / 4;
   long grid = (long)c->sm_count * c->ctas_c;
   if (grid * NW > nwt) grid = (nwt + NW - 1) / NW;
+  if (ESS) io.e2n = c->d_e2n_ess;
   k_grad_mult_pa_c<NW, STAGES, ESS, false, true><<<(unsigned)grid, NW * 32, smem, st>>>(c->tmap, x, c->d_yE, io, c->cfg.nelems,
                                                                                         c->grad_dt, nullptr, c->d_xend, HaloArgs{});
   POST_LAUNCH(c);
@@ -224,6 +227,7 @@ static int launch_gmc_halo(exab200_ctx* c, const double* x, double* y, ElemIO io
     CK(cudaFuncSetAttribute(k_grad_mult_pa_c<NW, STAGES, ESS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
+  if (ESS) io.e2n = c->d_e2n_ess;
   const long nwt = (c->cfg.nelems + 3) / 4;
   long compute = (long)c->sm_count * c->ctas_c - h.ncomm;   // the exchange CTAs take the place of compute CTAs: one wave
   if (compute * NW > nwt) compute = (nwt + NW - 1) / NW;
@@ -437,6 +441,7 @@ void exab200_destroy(exab200_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_e2n);
   cudaFree(c->d_ess);
+  cudaFree(c->d_e2n_ess);
   cudaFree(c->d_fail);
   cudaFree(c->d_k1_idle);
   cudaFree(c->d_halo_cnt);
@@ -485,6 +490,14 @@ int exab200_set_essential_mask(exab200_ctx* c, const unsigned char* h_mask) {
     c->have_ess = false;
     for (long i = 0; i < c->cfg.nnodes; ++i)
       if (h_mask[i] & 7) { c->have_ess = true; break; }
+    if (c->have_ess) {
+      if (c->cfg.nnodes > (long)kEssNodeMask) return fail("more than 2^28 nodes in one context");
+      const long n = 8 * c->cfg.nelems;
+      if (!c->d_e2n_ess) CK(cudaMalloc(&c->d_e2n_ess, sizeof(int) * n));
+      k_fold_ess_mask<<<(unsigned)((n + 255) / 256), 256>>>(c->d_e2n, c->d_ess, c->d_e2n_ess, n);
+      POST_LAUNCH(c);
+      CK(cudaDeviceSynchronize());
+    }
   } else {
     CK(cudaMemset(c->d_ess, 0, c->cfg.nnodes));
     c->have_ess = false;

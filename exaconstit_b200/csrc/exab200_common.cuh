@@ -39,34 +39,42 @@ __device__ __forceinline__ void nodal_to_qp_grad(double u, int lane, double& gx,
   gz = sz * (II - oII);
 }
 
-// Same transforms with the lane's three signs hoisted by the caller (persistent kernels: computed once per thread)
-struct LaneSigns { double sx, sy, sz; };
+// Same transforms with the lane's three signs hoisted by the caller (persistent kernels: computed once per thread).
+// A sign is kept as the bit to XOR into the high word (0 for +1, 0x80000000 for -1): the flip is one integer LOP3
+// instead of a DMUL on the fp64 pipe, bit-identical to the multiplication by +-1.0 (27 per element and lane in K2).
+struct LaneSigns { unsigned sx, sy, sz; };
 __device__ __forceinline__ LaneSigns lane_signs(int lane) {
-  return LaneSigns{(lane & 1) ? 1.0 : -1.0, (lane & 2) ? 1.0 : -1.0, (lane & 4) ? 1.0 : -1.0};
+  return LaneSigns{(lane & 1) ? 0u : 0x80000000u, (lane & 2) ? 0u : 0x80000000u, (lane & 4) ? 0u : 0x80000000u};
+}
+__device__ __forceinline__ double flip(double v, unsigned m) {
+  return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v));
 }
 __device__ __forceinline__ void nodal_to_qp_grad(double u, const LaneSigns& sg, double& gx, double& gy, double& gz) {
   double o = shfl_xor_d(u, 1);
   const double I = kAlpha * u + kBeta * o;
-  const double D = sg.sx * (u - o);
+  const double D = flip(u - o, sg.sx);
   double oI = shfl_xor_d(I, 2), oD = shfl_xor_d(D, 2);
   const double II = kAlpha * I + kBeta * oI;
   const double DI = kAlpha * D + kBeta * oD;
-  const double ID = sg.sy * (I - oI);
+  const double ID = flip(I - oI, sg.sy);
   const double oII = shfl_xor_d(II, 4), oDI = shfl_xor_d(DI, 4), oID = shfl_xor_d(ID, 4);
   gx = kAlpha * DI + kBeta * oDI;
   gy = kAlpha * ID + kBeta * oID;
-  gz = sg.sz * (II - oII);
+  gz = flip(II - oII, sg.sz);
 }
+// Transpose with 6 double shuffles instead of 8: in the y and x stages the partner combines what this lane needs of
+// it into ONE value before sending (the partner's sign is the opposite of this lane's, so it can apply it itself).
 __device__ __forceinline__ double qp_grad_to_nodal(double tx, double ty, double tz, const LaneSigns& sg) {
   const double otx = shfl_xor_d(tx, 4), oty = shfl_xor_d(ty, 4), otz = shfl_xor_d(tz, 4);
   const double DI = kAlpha * tx + kBeta * otx;
-  const double ID = kAlpha * ty + kBeta * oty;
-  const double II = sg.sz * (tz + otz);
-  const double oDI = shfl_xor_d(DI, 2), oID = shfl_xor_d(ID, 2), oII = shfl_xor_d(II, 2);
-  const double I = kAlpha * II + kBeta * oII + sg.sy * (ID + oID);
-  const double D = kAlpha * DI + kBeta * oDI;
-  const double oI = shfl_xor_d(I, 1), oD = shfl_xor_d(D, 1);
-  return kAlpha * I + kBeta * oI + sg.sx * (D + oD);
+  const double sID = flip(kAlpha * ty + kBeta * oty, sg.sy);  // sy * ID
+  const double II = flip(tz + otz, sg.sz);
+  // I = alpha II + sy ID + [beta II_p + sy ID_p], and sy ID_p = -(sy_p ID_p)
+  const double rI = shfl_xor_d(kBeta * II - sID, 2), oDI = shfl_xor_d(DI, 2);
+  const double I = kAlpha * II + sID + rI;
+  const double sD = flip(kAlpha * DI + kBeta * oDI, sg.sx);  // sx * D
+  const double r = shfl_xor_d(kBeta * I - sD, 1);
+  return kAlpha * I + sD + r;
 }
 
 // Transpose of the above: per-quadrature-point (t_xi, t_eta, t_zeta) -> nodal value

@@ -22,6 +22,17 @@ struct ElemIO {
   const unsigned char* __restrict__ essmask;  // nnodes or nullptr (LVEC)
   long nnodes;
 };
+// connectivity with the essential-dof bits folded in (k_grad_mult_pa_c<..., ESS = true>): node | mask << 28
+constexpr int kEssShift = 28;
+constexpr int kEssNodeMask = (1 << kEssShift) - 1;
+__global__ void __launch_bounds__(256) k_fold_ess_mask(const int* __restrict__ e2n, const unsigned char* __restrict__ ess,
+                                                       int* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int nd = e2n[i];
+    out[i] = nd | ((int)(ess[nd] & 7) << kEssShift);
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // K2: gradient (tangent-stiffness) operator apply, y += K x, matrix-free from the 6x6 material
@@ -481,16 +492,19 @@ __global__ void __launch_bounds__(NW * 32, 12 / NW) k_grad_mult_pa_c(const __gri
       if (t < nwt) issue(tile_of(t), s);
   }
 
+  // With ESS the connectivity entries carry the node's essential-dof bits in bits 28..30 (kEssShift; written by
+  // k_fold_ess_mask when the mask is set): one scattered byte gather less per lane and tile -- the kernel is bound by
+  // the L1TEX data-pipe wavefronts (shuffles + LDS + gathers + reds: 87 % of peak in ncu), not by instruction issue.
   auto load_nid = [&](long it) -> int {
     if (it >= nwt) return -1;
     const long e = (tile_of(it) << 2) + el;
     if (e >= nelems) return -1;
     return io.e2n[e * 8 + lex_to_native(lane)];
   };
-  auto load_x = [&](int nid, unsigned& msk, double& x0, double& x1, double& x2, double& c0, double& c1, double& c2) {
+  auto load_x = [&](int& nid, unsigned& msk, double& x0, double& x1, double& x2, double& c0, double& c1, double& c2) {
     msk = 0; x0 = x1 = x2 = 0.0; c0 = c1 = c2 = 0.0;
     if (nid < 0) return;
-    if (ESS) msk = io.essmask[nid];
+    if (ESS) { msk = (unsigned)nid >> kEssShift; nid &= kEssNodeMask; }
     x0 = x[nid]; x1 = x[io.nnodes + nid]; x2 = x[2 * io.nnodes + nid];
     c0 = xend[nid]; c1 = xend[io.nnodes + nid]; c2 = xend[2 * io.nnodes + nid];
   };
