@@ -7,7 +7,9 @@ from collections import defaultdict
 
 def main(path):
     rows = []
-    with open(path, newline="") as f:
+    import gzip
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rt", newline="") as f:
         lines = [l for l in f if l.startswith('"')]
     rd = csv.reader(lines)
     hdr = next(rd)
