@@ -123,42 +123,6 @@ EXAB_HD void compact_apply(const double* __restrict__ rec, const double* eps, do
   S[4] = sqr2i * w[3] - rec[30] * tr;
   S[5] = sqr2i * w[2] - rec[31] * tr;
 }
-// The same product with the record consumed in two halves (rec[0..15], rec[16..31]): what the half-box pipeline of the
-// PA gradient apply needs.  Same operation order as compact_apply (bit-identical results).
-EXAB_HD void compact_strain_vec(const double* eps, double* v, double& tr) {
-  v[0] = sqr2i * (eps[0] - eps[1]);
-  v[1] = sqr6i * (2.0 * eps[2] - eps[0] - eps[1]);
-  v[2] = sqr2i * eps[5];
-  v[3] = sqr2i * eps[4];
-  v[4] = sqr2i * eps[3];
-  tr = eps[0] + eps[1] + eps[2];
-}
-EXAB_HD void compact_apply_lo(const double* __restrict__ ra, const double* v, double* w) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    double t = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b) t += ra[a * 5 + b] * v[b];
-    w[a] = t;
-  }
-  w[3] = 0.0 + ra[15] * v[0];
-}
-EXAB_HD void compact_apply_hi(const double* __restrict__ rb, const double* v, double tr, double* w, double* S) {
-  double t = w[3];
-#pragma unroll
-  for (int b = 1; b < 5; ++b) t += rb[b - 1] * v[b];
-  w[3] = t;
-  t = 0.0;
-#pragma unroll
-  for (int b = 0; b < 5; ++b) t += rb[4 + b] * v[b];
-  w[4] = t;
-  S[0] = sqr2i * w[0] - sqr6i * w[1] + (rb[9] - rb[10]) * tr;
-  S[1] = -sqr2i * w[0] - sqr6i * w[1] + (rb[9] - rb[11]) * tr;
-  S[2] = sqr2b3 * w[1] + (rb[9] - rb[12]) * tr;
-  S[3] = sqr2i * w[4] - rb[13] * tr;
-  S[4] = sqr2i * w[3] - rb[14] * tr;
-  S[5] = sqr2i * w[2] - rb[15] * tr;
-}
 // the Voigt 6x6 at K36[j*6+i] = d sigma_i / d eps_j from the compact record
 EXAB_HD void compact_expand(const double* __restrict__ rec, double* K36) {
 #pragma unroll
