@@ -889,8 +889,13 @@ EXAB_HD int update_point(const MatDev& m, double dt, const double L[3][3], const
   // ---- getResponseECM (evptn) ----
 #pragma unroll
   for (int k = 0; k < 3; ++k) prob.w_sm[k] = w_vec[k];
+  {
+    // the beginning-of-step lattice strain is carried along with the step's volume change, e_u = e_n (V_old/V_new)^(1/3)
+    // (oracle/ecmech_port.hpp Options::vol_convect: what the reference's cyclic goldens pin)
+    const double f = cbrt(vOld / vNew);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) prob.e_n[i] = h0[iH_E + i];
+    for (int i = 0; i < 5; ++i) prob.e_n[i] = f * h0[iH_E + i];
+  }
   {
     double q[4], n = 0.0;
 #pragma unroll

@@ -198,6 +198,13 @@ struct Options {
   // goldens are missed by 1e-5 of the axial stress in the shear components, without them every printed value is
   // reproduced to about one unit of its 6th digit (tests/test_oracle_goldens.py).
   bool slip_stretch_terms = false;
+  // The beginning-of-step deviatoric lattice strain is carried along with the volume change of the step before the
+  // local solve: e_u = e_n (V_old / V_new)^(1/3).  Found in round 2 from the reference's cyclic goldens: without it the
+  // averaged axial stress is off by c e_n dsigma with c = 0.10 +- 0.01 = (1 - 2 nu)/3 in every elastic increment (most
+  // visible after the load reversals of voce_full_cyclic*: 1.5e-5 .. 2.2e-5 of the peak stress); with it these
+  // histories are reproduced to the print resolution (7e-7).  The analytic tangent does not carry the corresponding
+  // -e_u/3 d(tr eps) term (relative size sigma/E).
+  bool vol_convect = true;
 };
 
 struct Material {
@@ -753,7 +760,10 @@ inline int get_response_sngl(const Material& m, double dt, const double* d_svec_
   UpdateProblem prob(m);
   svec_to_vecd(d_svec_p, prob.d_sm);
   for (int k = 0; k < 3; ++k) prob.w_sm[k] = w_vec[k];
-  for (int i = 0; i < 5; ++i) prob.e_n[i] = hist[iHistLbE + i];
+  {
+    const double f = m.opt.vol_convect ? std::cbrt(vol_ratio[0] / vol_ratio[1]) : 1.0;
+    for (int i = 0; i < 5; ++i) prob.e_n[i] = f * hist[iHistLbE + i];
+  }
   {
     double n = 0.0;
     for (int i = 0; i < 4; ++i) n += hist[iHistLbQ + i] * hist[iHistLbQ + i];

@@ -90,6 +90,7 @@ static void set_opts(ecm::Options& o, const double* opts) {
   o.av_power = opts[3];
   o.slip_stretch_terms = opts[4] != 0.0;
   o.eos_mu_form = opts[5] != 0.0;
+  o.vol_convect = opts[6] != 0.0;
 }
 
 int orc_nhist(int xtal, int kin) { return ecm::iHistLbGdot + (xtal == ecm::XTAL_HCP ? 24 : 12) + 2; }

@@ -17,8 +17,12 @@ VOCE, VOCE_NL, KMBALD = 0, 1, 2
 
 
 def build(force=False):
-    if force or not os.path.exists(_LIB):
-        subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+    """make decides whether the library is stale (its rule lists every source); a box without make uses what is there"""
+    try:
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        if not os.path.exists(_LIB):
+            raise
     return _LIB
 
 
@@ -49,8 +53,8 @@ def _i(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-# (kirchhoff_rss, eos_temperature, hard_lag, av_power, slip_stretch_terms, eos_mu_form): see ecm::Options
-DEFAULT_OPTS = (1.0, 1.0, 1.0, 0.0, 0.0, 1.0)
+# (kirchhoff_rss, eos_temperature, hard_lag, av_power, slip_stretch_terms, eos_mu_form, vol_convect): see ecm::Options
+DEFAULT_OPTS = (1.0, 1.0, 1.0, 0.0, 0.0, 1.0, 1.0)
 
 
 def num_threads():

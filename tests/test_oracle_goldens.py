@@ -1,13 +1,15 @@
 """The oracle pinned against the reference's own golden outputs (test/data/*_stress.txt, checked by
 test/test_mechanics.py:11-31,49-54).  The goldens print 6 significant digits.
 
-Status ('Oracle and parity status'):
-  * FCC/BCC Voce and Voce-NL under monotonic loading (voce_pa, voce_ea, voce_full, voce_nl_full, voce_bcc, voce_ea_cs):
-    every printed axial stress is reproduced to within ONE unit of its 6th digit (<= 1.4e-6 relative) and every other
-    component to <= 2e-8 of the axial stress -- i.e. to the print resolution; the reference's own criterion
-    (identical printed digits) is missed only by last-digit rounding flips.
-  * KMBalD (mtsdd_bcc, mtsdd_full): 1.4e-5 / 7.5e-6 of the peak axial stress (transition regime), shear 8e-8.
-  * load reversals (voce_full_cyclic*): 2.2e-5 of the peak stress (the elastic unloading branch).
+Status ('Oracle and parity status'), with the volume-convected lattice strain found in round 2
+(oracle/ecmech_port.hpp Options::vol_convect):
+  * FCC/BCC Voce and Voce-NL (voce_pa, voce_ea, voce_full, voce_nl_full, voce_bcc, voce_ea_cs), BCC KMBalD (mtsdd_bcc)
+    and the load reversals (voce_full_cyclic*): every printed axial stress within HALF a unit of its 6th digit
+    (<= 1e-6 of the peak, 4e-6 for mtsdd_bcc), every other component <= 1e-8 / 9e-8: the printed values are identical,
+    and voce_pa / voce_full / voce_nl_full / voce_bcc / mtsdd_bcc PASS the reference's own criterion
+    (test/test_mechanics.py:11-31: mean absolute row difference of the 6-digit prints <= 1e-10) -- see
+    test_reference_pass_criterion.  The cyclic and EA cases miss it by the solver-noise columns only (1.2e-10 .. 3.9e-10).
+  * FCC KMBalD (mtsdd_full): axial 1.0e-6 (0.83 units), shear components up to two units of their last digit (2.8e-8).
 """
 import math
 
@@ -41,10 +43,24 @@ def golden_errors(s, gold):
 
 
 # per case: steps run in the default suite, and the bounds (axial in last-digit units or None, axial / peak, shear / peak)
-VOCE = dict(zz_ulp=1.25, zz=3.0e-6, shear=6.0e-8)
-KMBALD = dict(zz_ulp=None, zz=1.6e-5, shear=1.5e-7)
+VOCE = dict(zz_ulp=0.6, zz=1.2e-6, shear=2.0e-8)
+KMBALD = dict(zz_ulp=1.0, zz=5.0e-6, shear=6.0e-8)
 CASES = [("voce_pa", 40, VOCE), ("voce_ea", 8, VOCE), ("voce_full", 8, VOCE), ("voce_nl_full", 6, VOCE), ("voce_bcc", 40, VOCE),
          ("voce_ea_cs", 40, VOCE), ("mtsdd_bcc", 40, KMBALD), ("mtsdd_full", 40, KMBALD)]
+
+
+def reference_criterion(s, gold):
+    """check_stress of test/test_mechanics.py:11-31 applied to our rows printed the way the reference prints them
+    (Vector::Print with the stream's default 6 significant digits): sum of absolute differences over all six columns,
+    averaged over the rows; the reference passes a case when this is <= 1e-10."""
+    err = 0.0
+    for a, t in zip(gold, s):
+        for x, y in zip(a, t):
+            err += abs(float(x) - float("%.6g" % y))
+    return err / len(gold)
+
+
+REF_PASS = ("voce_pa", "voce_bcc", "mtsdd_bcc")   # whole histories in the default suite
 
 
 def _check(r, gold, lim):
@@ -60,6 +76,10 @@ def _check(r, gold, lim):
 def test_monotonic_goldens(orc, name, nsteps, lim):
     r, gold = _run(orc, name, nsteps)
     _check(r, gold, lim)
+    if name in REF_PASS:
+        # THE REFERENCE'S OWN PASS CRITERION on the whole history (measured 2.1e-11 / 1.9e-11 / 1.1e-11)
+        assert nsteps == len(gold) == 40
+        assert reference_criterion(r["stress"], gold) <= 1.0e-10
     if name == "voce_pa":
         # iteration counts are part of the parity record (reference = identity-preconditioned CG)
         assert r["stats"]["newton_iters"] < 120
@@ -71,6 +91,8 @@ def test_monotonic_goldens_whole_history(orc, name, lim):
     """the remaining 40-row histories (same material point physics as voce_pa through other operator paths)"""
     r, gold = _run(orc, name, 40)
     _check(r, gold, lim)
+    if name != "voce_ea":   # voce_ea: 1.2e-10, the golden's solver-noise columns
+        assert reference_criterion(r["stress"], gold) <= 1.0e-10
 
 
 def test_printed_digits_of_voce_pa(orc):
@@ -87,8 +109,7 @@ def test_printed_digits_of_voce_pa(orc):
             d = abs(float("%.6g" % s[i, c]) - gold[i, c]) / _ulp6(gold[i, c])
             off += d > 0.5
             worst = max(worst, d)
-    assert worst <= 1.5, worst          # at most the last digit, by one
-    assert off <= 50, off               # about 40 of 150 at this commit
+    assert off == 0 and worst <= 0.5, (off, worst)   # all 152 printed values identical (about 40 differed in round 1)
 
 
 def test_plastic_work_and_dp_goldens(orc):
@@ -123,8 +144,8 @@ def test_cyclic_reversal(orc):
     r = orc.sim_run(**inp)
     assert r["rc"] == 0
     err = np.abs(r["stress"][:, 2] - gold[:14, 2]).max() / np.abs(gold[:14, 2]).max()
-    assert err < 2.5e-5, err
-    assert np.abs(r["stress"][:, 3:] - gold[:14, 3:]).max() / np.abs(gold[:14, 2]).max() < 5e-7
+    assert err < 1.5e-6, err          # 1.5e-5 before the volume-convected strain
+    assert np.abs(r["stress"][:, 3:] - gold[:14, 3:]).max() / np.abs(gold[:14, 2]).max() < 3e-8
 
 
 def test_constant_strain_rate_bcs(orc):
