@@ -68,3 +68,16 @@ def test_our_arm_refuses_to_run_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0          # no CPU fallback: the CUDA path is the only path
     assert r.stdout.strip() == ""
+
+
+def test_fingerprint_covers_the_driver_run():
+    """bench.py compares every run with the stored 1-GPU history (parity_fingerprint): the driver's
+    `--steps 20 --warmup 5` needs 25 stored steps of the default workload, each with six stress components."""
+    import json
+    import bench
+    fp = json.load(open(bench.FINGERPRINT))
+    n = 128
+    g, _ = bench.grains_for(n)
+    ent = fp["%d:%d:1000:0" % (n, g)]
+    assert len(ent["avg_stress"]) >= 25 and len(ent["newton_iters"]) == len(ent["avg_stress"])
+    assert all(len(row) == 6 for row in ent["avg_stress"])
